@@ -1,0 +1,291 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI, via the Python mirror) against the NumPy oracle
+on identical seeded inputs.  Tolerances follow BASELINE.json north_star: argmax bit-exact; logits,
+gradients and singular values within 1e-4 relative (FP32).  Node tensors are only compared through
+gauge-invariant quantities."""
+import numpy as np
+import pytest
+import torch
+
+import trmps_oracle as o
+import trmps_native as nat
+import trmps_device as dev
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def cuda():
+    return torch.device("cuda", 0)
+
+
+def make_case(N, B, L, max_size, seed, fm=o.FM_ONE_SQRT3, full_bond=None, loc=None):
+    pix, lab = o.synthetic_batch(N, B, L, seed=seed)
+    phi = o.feature_map(pix, fm)
+    if full_bond:
+        loc = 0 if loc is None else loc
+        nodes = o.random_full_bond_mps(N, 2, L, full_bond, loc=loc, seed=seed + 1)
+    else:
+        nodes, loc = o.initial_nodes(N, 2, L, loc=loc)
+    return pix, phi, lab, nodes, loc
+
+
+def make_state(N, B, L, max_size, nodes, loc, feat, lab, fm=nat.FM_PRECOMPUTED, loss=nat.LOSS_SOFTMAX_XENT):
+    Ds = dev.bond_stride(nodes, loc, L, max_size)
+    st = dev.SweepState(N, B, L, Ds, fm, loss, cuda())
+    st.set_nodes(nodes, loc)
+    st.set_batch(feat, lab)
+    return st
+
+
+# --------------------------------------------------------------------------------------------- env / predict
+@pytest.mark.parametrize("D,B", [(20, 300), (24, 1000), (56, 257), (120, 300)])
+def test_env_step_both_directions(D, B):
+    rng = np.random.default_rng(D)
+    L = 10
+    Ds = dev.align8(max(D, 2 * L))
+    Dl, Dr = D, max(3, D - 5)
+    node = rng.normal(size=(2, Dl, Dr)).astype(np.float32)
+    phi = o.feature_map(rng.random((1, B), dtype=np.float32), o.FM_ONE_SQRT3)[0]
+    lib = nat.load()
+    slot = np.zeros((2, Ds, Ds), np.float32)
+    slot[:, :Dl, :Dr] = node
+    for direction, din, dout in ((+1, Dl, Dr), (-1, Dr, Dl)):
+        env = np.zeros((B, Ds), np.float32)
+        env[:, :din] = rng.normal(size=(B, din)).astype(np.float32)
+        want = o.chain_right(env[:, :Dl], phi, node) if direction > 0 else o.chain_left(env[:, :Dr], phi, node)
+        t_env, t_slot, t_phi = (torch.from_numpy(x).cuda() for x in (env, slot, phi))
+        t_din = torch.tensor([din], dtype=torch.int32, device="cuda")
+        out = torch.full((B, Ds), 7.0, device="cuda")
+        nat.check(lib.trmps_env_step(t_phi.data_ptr(), nat.FM_PRECOMPUTED, B, Ds, direction, t_env.data_ptr(),
+                                     t_slot.data_ptr(), t_din.data_ptr(), out.data_ptr(), None), "env_step")
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        assert rel(got[:, :dout], want) < 2e-6
+        assert np.all(got[:, dout:] == 0)          # padding stays zero
+
+
+@pytest.mark.parametrize("fm", [o.FM_ONE_SQRT3, o.FM_ONE_X, o.FM_COS_SIN])
+def test_fused_feature_map_matches_precomputed(fm):
+    N, B, L = 12, 500, 10
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=3, fm=fm)
+    w = dev.DeviceWeights(nodes, loc, L, dev.bond_stride(nodes, loc, L), cuda())
+    a = dev.predict(w, torch.from_numpy(pix).cuda(), fm).cpu().numpy()
+    b = dev.predict(w, torch.from_numpy(phi).cuda(), nat.FM_PRECOMPUTED).cpu().numpy()
+    want = o.predict(nodes, loc, phi, L)
+    assert rel(b, want) < 1e-5
+    assert rel(a, want) < 1e-5
+
+
+@pytest.mark.parametrize("N,B,D,loc", [(16, 333, None, None), (16, 200, None, 0), (16, 200, None, 15),
+                                       (20, 1000, 32, 7), (12, 129, 120, 0)])
+def test_predict_matches_oracle(N, B, D, loc):
+    L = 10
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=11, full_bond=D, loc=loc)
+    w = dev.DeviceWeights(nodes, loc, L, dev.bond_stride(nodes, loc, L), cuda())
+    got = dev.predict(w, torch.from_numpy(phi).cuda(), nat.FM_PRECOMPUTED).cpu().numpy()
+    want32 = o.predict(nodes, loc, phi, L)
+    want64 = o.predict([n.astype(np.float64) for n in nodes], loc, phi.astype(np.float64), L)
+    assert rel(got, want64) < RTOL
+    assert rel(got, want64) < 10 * max(rel(want32, want64), 1e-7)
+    margin = np.sort(want64, axis=1)
+    clear = (margin[:, -1] - margin[:, -2]) > 1e-5 * np.abs(margin[:, -1])
+    assert np.array_equal(got.argmax(1)[clear], want64.argmax(1)[clear])      # argmax bit-exact
+
+
+def test_predict_round_and_mirror_class():
+    from mps.mps import MPS
+    N, B, L = 10, 64, 10
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=5)
+    net = MPS(2, L, N, round=True)
+    net.prepare()
+    f = net.predict(phi)
+    assert np.array_equal(f, np.round(o.predict(nodes, loc, phi, L)))
+    assert isinstance(f, np.ndarray) and f.shape == (B, L)
+    ft = MPS(2, L, N)
+    ft.prepare()
+    out = ft.predict(torch.from_numpy(phi).cuda())
+    assert isinstance(out, torch.Tensor) and out.is_cuda
+
+
+# --------------------------------------------------------------------------------------------- bond pieces
+def oracle_bond_setup(nodes, loc, phi, L, direction):
+    C1s, C2s = o.setup_environments(nodes, loc, phi, L)
+    if direction > 0:
+        bond = np.einsum('lmij,njk->lmnik', nodes[loc], nodes[loc + 1])
+        args = (C1s[loc], C2s[loc + 1], phi[loc], phi[loc + 1])
+    else:
+        C2s[loc] = o.chain_left(C2s[loc + 1], phi[loc + 1], nodes[loc + 1])
+        bond = np.einsum('nkj,lmji->lmnik', nodes[loc - 1], nodes[loc])
+        args = (C2s[loc], C1s[loc - 1], phi[loc], phi[loc - 1])
+    return bond, args
+
+
+def state_bond(st, M=None):
+    return st.bond_tensor(M).cpu().numpy()
+
+
+@pytest.mark.parametrize("direction", [+1, -1])
+@pytest.mark.parametrize("D", [None, 24, 40])
+def test_merge_forward_gradient(direction, D):
+    N, B, L = 10, 700, 10
+    loc = 4
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=21, full_bond=D, loc=loc)
+    if D is None:
+        nodes = [n + 0.01 * np.random.default_rng(i).normal(size=n.shape).astype(np.float32) for i, n in enumerate(nodes)]
+    st = make_state(N, B, L, D or 24, nodes, loc, phi, lab)
+    st.init_env(loc)
+    if direction < 0:   # the left move at loc needs C2s[loc]: build it from loc+1
+        lib = nat.load()
+        nat.check(lib.trmps_env_step(st.feat[loc + 1].data_ptr(), nat.FM_PRECOMPUTED, B, st.Ds, -1,
+                                     st.envR[loc + 1].data_ptr(), st.slots[loc + 1].data_ptr(),
+                                     st.dims[loc + 2:].data_ptr(), st.envR[loc].data_ptr(), None), "env_step")
+    bond, (Cn, Cf, pn, pf) = oracle_bond_setup(nodes, loc, phi, L, direction)
+    dn, df = bond.shape[3], bond.shape[4]
+    st.bond_merge(loc, direction)
+    got_bond = state_bond(st)[:, :, :, :dn, :df]
+    assert rel(got_bond, bond) < 1e-6
+    p = o.SweepParams(max_size=st.Ds, reg=0.01)
+    C = o.calculate_C(Cn, Cf, pn, pf)
+    h, cost0, f0 = o.get_f_and_cost(bond, C, lab, p)
+    opt = dev.make_opt(lr=0.1, max_size=st.Ds, reg=0.01)
+    st.bond_gradient(loc, direction, opt)
+    torch.cuda.synchronize()
+    assert rel(st.logits0().cpu().numpy(), f0) < 1e-5
+    G = np.tensordot(lab - h, C, axes=([0], [0])) - np.float32(2 * p.reg) * bond
+    C64 = C.astype(np.float64)
+    G64 = np.tensordot((lab - h).astype(np.float64), C64, axes=([0], [0])) - 2 * p.reg * bond.astype(np.float64)
+    gotG = state_bond(st, st.grad_matrix())[:, :, :, :dn, :df]
+    assert rel(gotG, G64) < RTOL
+    assert rel(gotG, G64) < 10 * max(rel(G, G64), 1e-7)
+    sc = st.scalars().cpu().numpy()
+    assert abs(sc[nat.S_COST0] - cost0) < 1e-5 * abs(cost0)
+    gdc = np.sum(G64 * G64) / B
+    assert abs(sc[nat.S_GDC] - gdc) < 1e-4 * gdc
+    # padding of the gradient stays zero
+    full = state_bond(st, st.grad_matrix())
+    full[:, :, :, :dn, :df] = 0
+    assert np.all(full == 0)
+
+
+# --------------------------------------------------------------------------------------------- split (SVD)
+@pytest.mark.parametrize("direction", [+1, -1])
+@pytest.mark.parametrize("D,max_size", [(None, 24), (24, 24), (40, 32)])
+def test_split_matches_lapack(direction, D, max_size):
+    N, B, L, loc = 6, 64, 10, 3
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=31, full_bond=D, loc=loc)
+    st = make_state(N, B, L, max(max_size, D or 0), nodes, loc, phi, lab)
+    st.bond_merge(loc, direction)
+    bond, _ = oracle_bond_setup(nodes, loc, phi, L, direction)
+    p = o.SweepParams(max_size=max_size, min_singular_value=1e-4)
+    tr = o.Trace(); tr.append({})
+    a_j, a_j1 = o.bond_decomposition(bond, p, tr)
+    opt = dev.make_opt(lr=0.1, max_size=max_size, min_singular_value=1e-4)
+    st.bond_split(loc, direction, opt)
+    torch.cuda.synchronize()
+    iw = st.iwork.cpu().numpy()
+    m = int(iw[nat.I_M])
+    assert m == a_j.shape[2]
+    s_ref = tr[-1]['s']
+    sv = st.singular_values().cpu().numpy()
+    k = len(s_ref)
+    big = s_ref > 1e-3 * s_ref[0]
+    assert np.max(np.abs(sv[:k][big] - s_ref[big]) / s_ref[big]) < RTOL
+    assert np.max(np.abs(sv[:k] - s_ref)) < 1e-5 * s_ref[0]
+    # gauge-invariant: a_j . a_j1 equals the rank-m truncation computed by LAPACK
+    want = np.einsum('miq,qlnk->lmnik', a_j, a_j1)
+    nodes_new = st.get_nodes()
+    dims = st.dims.cpu().numpy()
+    if direction > 0:
+        node, sp = nodes_new[loc], st.special.cpu().numpy()[:, :, :m, :dims[loc + 2]]
+        got = np.einsum('miq,lnqk->lmnik', node, sp)
+        assert dims[loc + 1] == m
+        ortho = np.einsum('miq,mir->qr', node, node)
+    else:
+        node, sp = st.slots.cpu().numpy()[loc][:, :m, :dims[loc + 1]], st.special.cpu().numpy()[:, :, :dims[loc - 1], :m]
+        got = np.einsum('mqi,lnkq->lmnik', node, sp)
+        assert dims[loc] == m
+        ortho = np.einsum('mqi,mri->qr', node, node)
+    assert rel(got, want) < RTOL
+    assert np.max(np.abs(ortho - np.eye(m))) < 1e-5        # a_j has orthonormal columns
+
+
+# --------------------------------------------------------------------------------------------- full bond update / sweep
+@pytest.mark.parametrize("loss", [o.SOFTMAX_XENT, o.SQUARED])
+@pytest.mark.parametrize("updates", [1, 3])
+def test_bond_step_matches_oracle(loss, updates):
+    N, B, L, loc = 8, 400, 10, 3
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=41, loc=loc)
+    st = make_state(N, B, L, 24, nodes, loc, phi, lab, loss=loss)
+    st.init_env(loc)
+    lr = 0.05
+    p = o.SweepParams(max_size=24, updates_per_step=updates, loss_kind=loss)
+    C1s, C2s = o.setup_environments(nodes, loc, phi, L)
+    tr = o.Trace()
+    a_j, n1 = o.update_right(loc, nodes[loc], nodes, C1s, C2s, phi, lab, lr, p, tr)
+    st.bond_step(loc, +1, dev.make_opt(lr=lr, max_size=24, updates_per_step=updates))
+    torch.cuda.synchronize()
+    iw, sc = st.iwork.cpu().numpy(), st.scalars().cpu().numpy()
+    last = tr[-1]
+    assert int(iw[nat.I_ACCEPT]) == int(last['accepted'])
+    assert int(iw[nat.I_TRIALS]) == last['trials']
+    assert abs(sc[nat.S_COST0] - last['cost0']) < 1e-5 * abs(last['cost0'])
+    assert abs(sc[nat.S_COST1] - last['cost1']) < 1e-5 * abs(last['cost1'])
+    assert int(iw[nat.I_M]) == last['m']
+    k = len(last['s'])
+    sv = st.singular_values().cpu().numpy()[:k]
+    big = last['s'] > 1e-3 * last['s'][0]
+    assert np.max(np.abs(sv[big] - last['s'][big]) / last['s'][big]) < RTOL
+    m = last['m']
+    got_nodes = st.get_nodes()
+    got = np.einsum('miq,lnqk->lmnik', got_nodes[loc], got_nodes[loc + 1])
+    want = np.einsum('miq,lnqk->lmnik', a_j, n1)
+    assert rel(got, want) < RTOL
+    envL = st.envL[loc + 1].cpu().numpy()[:, :m]
+    # new environment: compare through the gauge-invariant product with the new special node
+    got_ctr = np.einsum('tq,lnqk->tlnk', envL, got_nodes[loc + 1])
+    want_ctr = np.einsum('tq,lnqk->tlnk', C1s[loc + 1], n1)
+    assert rel(got_ctr, want_ctr) < RTOL
+
+
+@pytest.mark.parametrize("N,B,max_size,loc", [(8, 300, 24, None), (10, 257, 32, 0)])
+def test_train_step_matches_oracle(N, B, max_size, loc):
+    L = 10
+    pix, phi, lab, nodes, loc = make_case(N, B, L, max_size, seed=51, loc=loc)
+    lr = 0.05
+    p = o.SweepParams(max_size=max_size)
+    tr = o.Trace()
+    want_nodes = o.train_step(nodes, loc, phi, lab, lr, p, L, tr)
+    want_f = o.predict(want_nodes, loc, phi, L)
+    st = make_state(N, B, L, max_size, nodes, loc, phi, lab)
+    st.train_step(dev.make_opt(lr=lr, max_size=max_size), loc=loc)
+    torch.cuda.synchronize()
+    got_nodes = st.get_nodes()
+    assert [w.shape for w in got_nodes] == [w.shape for w in want_nodes]
+    got_f = dev.predict(st.weights_view(), st.feat, nat.FM_PRECOMPUTED).cpu().numpy()
+    assert rel(got_f, want_f) < 1e-3          # 2(N-1) chained updates; per-update parity is pinned above
+    assert np.mean(got_f.argmax(1) == want_f.argmax(1)) > 0.995
+    iw = st.iwork.cpu().numpy()
+    assert int(iw[nat.I_N_UPDATES]) == len(tr) == 2 * (N - 1)
+    assert abs(o.cost(got_f, lab) - o.cost(want_f, lab)) < 1e-3 * o.cost(want_f, lab)
+
+
+def test_optimizer_class_train_runs_and_learns(tmp_path):
+    from trmps import MPS, MPSOptimizer, MPSOptimizerParameters, MPSTrainingParameters, SyntheticMNISTDatasource
+    ds = SyntheticMNISTDatasource(shrink=True, n_train=400, n_test=100, seed=1)
+    net = MPS(2, 10, 196)
+    net.prepare(ds, iterations=50, learning_rate=0.05)
+    opt = MPSOptimizer(net, 16, MPSOptimizerParameters(path=str(tmp_path / "cfg"), reg=1e-3))
+    f0 = net.predict(ds.test_data[0])
+    c0 = net.cost(f0, ds.test_data[1])
+    opt.train(ds, 400, 1, MPSTrainingParameters(rate_of_change=1e-2, verbose_save=False))
+    f1 = net.predict(ds.training_data[0])
+    assert len(opt.test) == 196
+    assert net.cost(f1, ds.training_data[1]) < c0
+    again = MPS.from_file(str(tmp_path / "cfg"))
+    assert rel(again.predict(ds.test_data[0]), net.predict(ds.test_data[0])) < 1e-6
