@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the TrMPS hot path on B200.
+
+Metric (BASELINE.json): sweep images*bonds/sec at N=196, D=120 (cfg3: 14x14 synthetic MNIST shape, d=2,
+10 labels, 60k images per GPU, full-bond initial MPS, feature map [cos, sin]).  One "step" = one full
+left-to-right half-sweep of N-1 = 195 two-site bond updates (merge, forward, gradient, Armijo, truncated
+Jacobi SVD split, environment advance) including the initial environment build.
+
+    python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference ...                     the reference arithmetic on the host CPU (oracle port)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "mps-mnist_b200", "trmps"))
+
+import numpy as np
+
+CFG = dict(N=196, D=120, L=10, d=2, B=60000)          # configs[2] of BASELINE.json ("cfg3")
+METRIC = "sweep_images_bonds_per_sec"
+UNIT = "images*bonds/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    bf16_burst=p["bf16_tflops"], source="measured")
+    return dict(hbm_gbs=6650.0, bf16_sustained=1400.0, bf16_burst=1590.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------ synthetic workload
+def synthetic_pixels(N, B, L, seed):
+    rng = np.random.default_rng(seed)
+    pixels = rng.random((N, B), dtype=np.float32)
+    cls = rng.integers(0, L, B)
+    labels = np.zeros((B, L), dtype=np.float32)
+    labels[np.arange(B), cls] = 1
+    return pixels, labels
+
+
+def full_bond_mps(N, d, L, D, loc, seed=1):
+    """Near-identity site tensors + N(0, (0.1/sqrt(D))^2) noise, all internal bonds = D."""
+    rng = np.random.default_rng(seed)
+    noise = 0.1 / np.sqrt(D)
+    dims = [2 * L] + [D] * (N - 1) + [2 * L]
+    nodes = []
+    for i in range(N):
+        dl, dr = dims[i], dims[i + 1]
+        base = np.zeros((d, dl, dr))
+        k = min(dl, dr)
+        base[0, :k, :k] = np.eye(k)
+        if i == loc:
+            node = 0.5 * base[None] + rng.normal(0.0, noise, size=(L, d, dl, dr))
+        else:
+            node = base + rng.normal(0.0, noise, size=(d, dl, dr))
+        nodes.append(node.astype(np.float32))
+    return nodes
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_sweep_rate(B_s, bonds, D, L, seed=0, reps=1):
+    """Times the oracle (literal restatement of the reference graph: materialised C, four contractions per
+    update, LAPACK SVD; oracle/trmps_oracle.py) on the host cores for `bonds` full-size bond updates on a
+    B_s-image sample.  Returns (images*bonds/s, seconds, cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import trmps_oracle as o
+    Nc = bonds + 3
+    loc = 1
+    pix, lab = synthetic_pixels(Nc, B_s, L, seed)
+    phi = o.feature_map(pix, o.FM_COS_SIN)
+    nodes = full_bond_mps(Nc, 2, L, D, loc)
+    p = o.SweepParams(max_size=D, min_singular_value=0.0)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        C1s, C2s = o.setup_environments(nodes, loc, phi, L)
+        o.sweep_right(nodes, loc, loc + bonds, C1s, C2s, phi, lab, 1e-3, p)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return B_s * bonds / best, best, os.cpu_count()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    B_s, bonds = args.cpu_sample_images, args.cpu_sample_bonds
+    for _ in range(args.warmup):
+        cpu_sweep_rate(min(B_s, 256), 1, CFG["D"], CFG["L"])
+    times, rates = [], []
+    for _ in range(args.steps):
+        r, dt, cores = cpu_sweep_rate(B_s, bonds, CFG["D"], CFG["L"])
+        times.append(dt); rates.append(r)
+    value = B_s * bonds * len(times) / sum(times)
+    sample = "%d images x %d full-size (D=%d) bond updates per step, literal reference graph in NumPy" % (B_s, bonds, CFG["D"])
+    out = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+               warmup=args.warmup, ms_per_step=1e3 * sum(times) / len(times), higher_is_better=True, scaling="weak",
+               vs_baseline=None, dtype="f32", data="synthetic",
+               config=dict(workload="cfg3 N=196 D=120 B=60000/GPU L->R half-sweep (bounded CPU sample)", sample=sample),
+               cpu_baseline=dict(value=value, unit=UNIT, cores=os.cpu_count(), kind="port", sample=sample),
+               e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import trmps_native as nat
+    import trmps_device as dev
+    from trmps import MPS, MPSOptimizer, MPSOptimizerParameters
+
+    nat.require_gpu(local_rank)
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    N, D, L, B = CFG["N"], CFG["D"], CFG["L"], args.images_per_gpu
+    bonds = N - 1
+    loc = 0
+    lr = 1e-3
+    pix, lab = synthetic_pixels(N, B, L, seed=100 + rank)
+    nodes = full_bond_mps(N, 2, L, D, loc)
+
+    net = MPS(2, L, N, special_node_loc=loc)
+    net.prepare(_weights=nodes)
+    params = MPSOptimizerParameters(min_singular_value=0.0, reg=1e-3, updates_per_step=1)
+    optim = MPSOptimizer(net, D, params)
+    optim.feature_map = nat.FM_COS_SIN
+    optim.rate_of_change = lr
+    if world > 1:
+        optim.attach_process_group()
+    pix_pin = torch.from_numpy(pix).pin_memory()
+    lab_pin = torch.from_numpy(lab).pin_memory()
+    optim.bind_batch(pix_pin, lab_pin, weights=nodes)
+    st = optim._state
+    opt = optim._opt(lr)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def device_step():
+        # inputs already resident in HBM: reset weights from a device copy, build environments, sweep L->R
+        st.slots.copy_(slots0); st.special.copy_(special0); st.dims.copy_(dims0)
+        st.loc = loc
+        st.init_env(loc)
+        st.sweep(loc, N - 1, +1, opt)
+
+    slots0, special0, dims0 = st.slots.clone(), st.special.clone(), st.dims.clone()
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    nat.profile_begin(200000)
+    l0 = nat.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        device_step()
+    ev1.record()
+    barrier()
+    launches = nat.launch_count() - l0
+    prof = nat.profile_end()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * B * bonds * args.steps / (ms_total * 1e-3)
+    iw = st.iwork.cpu().numpy()
+
+    # end-to-end through the public Python API with HOST buffers: H2D of the batch and the weights, sweep, D2H of the weights
+    def e2e_step():
+        optim.bind_batch(pix_pin, lab_pin, weights=nodes)
+        optim._setup_optimization()
+        optim._sweep_right(loc, N - 1)
+        out_nodes = optim.updated_nodes()
+        cost = float(st.scalars()[nat.S_COST1].item())
+        return out_nodes, cost
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        out_nodes, last_cost = e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * bonds * args.e2e_steps / float(e2e_s.item())
+    h2d = pix.nbytes + lab.nbytes + sum(w.nbytes for w in nodes)
+    d2h = sum(w.nbytes for w in out_nodes) + 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    tf32_peak = peaks["bf16_sustained"] / 2.0       # TF32 dense = bf16 / 2, kernel timed inside a long step
+    fwd_ms, fwd_n = prof["forward"]
+    flops_per_launch = 2.0 * B * L * 4 * D * D     # one 2*L*d^2*Dl*Dr contraction per image
+    # the first bond has Dl = 2L < D; count its launches at their true size
+    fwd_flops_total = (fwd_n - 2 * args.steps) * flops_per_launch + 2 * args.steps * 2.0 * B * L * 4 * (2 * L) * D
+    achieved = fwd_flops_total / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else 0.0
+    breakdown = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
+    out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+               ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+               data="synthetic",
+               config=dict(workload="cfg3: N=196 D=120 L=10 d=2, %d images per GPU, one L->R half-sweep (195 bond updates, "
+                                    "init env build included), feature map cos/sin, full-bond random MPS, min_sv=0" % B,
+                           images_per_gpu=B, global_batch=B * world, bonds_per_step=bonds, parallelism="dp%d" % world,
+                           l2="inputs larger than L2 (environment caches %.1f GB per GPU)" % (2 * N * B * D * 4 / 1e9),
+                           realised_m=int(iw[nat.I_M]), updates=int(iw[nat.I_N_UPDATES]), reverts=int(iw[nat.I_N_REVERT])),
+               clocks=clocks, gpu_launches=int(launches),
+               e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                        steps=args.e2e_steps, last_cost=last_cost),
+               roofline=dict(kernel="forward_kernel (f(bond) and f(delta): 2 of the 3 dense contractions per update)",
+                             bound="tensor", achieved=achieved, peak=tf32_peak, unit="TFLOP/s",
+                             frac=achieved / tf32_peak, traffic=None, peak_source="%s bf16 sustained / 2 (TF32)" % peaks["source"],
+                             avg_launch_ms=fwd_ms / max(fwd_n, 1), launches=fwd_n),
+               breakdown_ms_per_step=breakdown)
+    if world == 1 and not args.no_cpu_baseline:
+        r, dt, cores = cpu_sweep_rate(args.cpu_sample_images, args.cpu_sample_bonds, D, L)
+        out["cpu_baseline"] = dict(value=r, unit=UNIT, cores=cores, kind="port",
+                                   sample="%d images x %d full-size bond updates (%.1f s), literal reference graph in NumPy"
+                                          % (args.cpu_sample_images, args.cpu_sample_bonds, dt))
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images-per-gpu", type=int, default=CFG["B"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample-images", type=int, default=2000)
+    ap.add_argument("--cpu-sample-bonds", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

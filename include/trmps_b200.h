@@ -105,7 +105,7 @@ typedef struct {
   int64_t hres;                          /* (B, 2L)  h(1-h)[t,l] * phi_far[t,n]^2 (Hessian only) */
   int64_t phi2;                          /* 2 x (B, 2) feature vectors of the near and far site */
   int64_t Ut;                            /* R x R   rows = left singular vectors (U transposed) */
-  int64_t sv;                            /* R       singular values of the last split, descending */
+  int64_t sv;                            /* 3R: singular values (descending), int32 order, int32 row map */
   int64_t red;                           /* per-CTA partial sums of the scalar reductions */
   int64_t scal;                          /* TRMPS_S_COUNT floats */
   int64_t total;                         /* floats the caller must allocate for `work` */
@@ -152,6 +152,14 @@ typedef struct {
 int         trmps_abi_version(void);
 const char* trmps_last_error(void);
 int         trmps_device_check(int device);             /* TRMPS_OK if `device` is an sm_100 GPU */
+int64_t     trmps_launch_count(void);                   /* kernels launched by this library so far (process-wide) */
+
+/* optional device-side timing of the kernels a sweep launches (CUDA events on the caller's stream; replaces the
+ * tf.RunOptions(FULL_TRACE) timeline of baseoptimizer.py:82-86).  Categories: 0 env chain, 1 forward contraction,
+ * 2 gradient contraction, 3 SVD split, 4 bond merge, 5 scalar/elementwise, 6 all-reduce. */
+#define TRMPS_PROF_NCAT 7
+int trmps_profile_begin(int32_t max_records);
+int trmps_profile_end(float* ms_per_cat, int32_t* count_per_cat, int32_t ncat);   /* synchronises the recorded events */
 
 /* sizes */
 int     trmps_sweep_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, int32_t sm_count, trmps_layout* out);

@@ -20,9 +20,20 @@ int cuda_fail(cudaError_t e, const char* what);
 
 #define TRMPS_LAUNCH_OK(name)                                            \
   do {                                                                   \
+    ::trmps::count_launch();                                             \
     cudaError_t _e = cudaGetLastError();                                 \
     if (_e != cudaSuccess) return ::trmps::cuda_fail(_e, name);          \
   } while (0)
+
+void count_launch();
+
+// optional per-category device timing (CUDA events on the launching stream); off unless trmps_profile_begin was called
+enum ProfCat { PROF_ENV = 0, PROF_FORWARD, PROF_GRAD, PROF_SVD, PROF_MERGE, PROF_SCALAR, PROF_COMM, PROF_NCAT };
+struct ProfScope {
+  int cat; cudaStream_t st; bool on;
+  ProfScope(int cat, cudaStream_t st);
+  ~ProfScope();
+};
 
 __host__ __device__ __forceinline__ int align_up(int x, int a) { return (x + a - 1) / a * a; }
 __host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

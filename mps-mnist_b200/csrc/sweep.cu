@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -22,6 +23,31 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return TRMPS_E_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------ counters / profiling
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
+struct ProfRec { cudaEvent_t a, b; int cat; };
+static bool g_prof_on = false;
+static ProfRec* g_prof = nullptr;
+static int g_prof_n = 0, g_prof_cap = 0;
+
+ProfScope::ProfScope(int c, cudaStream_t s) : cat(c), st(s), on(false) {
+  if (!g_prof_on || g_prof_n >= g_prof_cap) return;
+  ProfRec& r = g_prof[g_prof_n];
+  if (!r.a) {
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  }
+  r.cat = c;
+  cudaEventRecord(r.a, st);
+  on = true;
+}
+ProfScope::~ProfScope() {
+  if (!on) return;
+  cudaEventRecord(g_prof[g_prof_n].b, st);
+  ++g_prof_n;
 }
 
 static int g_sm_count = 0;
@@ -87,7 +113,7 @@ static int compute_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, int32_t s
   o->hres = off; off += a4(B * 2 * L);
   o->phi2 = off; off += a4(4 * B);
   o->Ut = off; off += a4(R * R);
-  o->sv = off; off += a4(2 * R);
+  o->sv = off; off += a4(3 * R);
   int64_t rr = (B + 255) / 256;
   if (rr < 296) rr = 296;
   o->red = off; off += a4(rr * 32);
@@ -153,11 +179,13 @@ static int phi_pair(const trmps_sweep* s, const trmps_layout& lay, const BondGeo
 }
 
 static int do_merge(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, cudaStream_t st) {
+  ProfScope ps(PROF_MERGE, st);
   return launch_merge(s->special, s->nodes + (size_t)g.far_site * 2 * s->Ds * s->Ds, s->work + lay.bondM, s->Ds, s->L, g.dir,
                       g.d_mid, st);
 }
 
 static int do_forward(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const float* M, cudaStream_t st) {
+  ProfScope ps(PROF_FORWARD, st);
   const float* phi2 = s->work + lay.phi2;
   return launch_forward(g.e_near, g.e_far, phi2, phi2 + 2 * s->B, M, s->work + lay.fpart, lay.nsplit, s->B, s->Ds, s->L, 2,
                         g.d_near, st);
@@ -180,19 +208,29 @@ static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const Bond
   la.hres = hess ? w + lay.hres : nullptr; la.red = w + lay.red; la.B = s->B; la.L = L; la.loss_kind = s->loss_kind;
   la.from_parts = from_parts;
   int rc;
-  if ((rc = launch_loss(la, st))) return rc;
   const int nblk = (int)ceil_div64(s->B, 256);
   float* tail = w + lay.gradM + RC;
-  if ((rc = launch_sum_red(w + lay.red, nblk, 1, 1.0f, tail, st))) return rc;
-  if ((rc = launch_grad(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit, s->B, Ds, L, false, st))) return rc;
-  if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit, RC, w + lay.gradM, st))) return rc;
-  if ((rc = allreduce_sum(s->comm, w + lay.gradM, RC + 4, st))) return rc;
+  {
+    ProfScope ps(PROF_SCALAR, st);
+    if ((rc = launch_loss(la, st))) return rc;
+    if ((rc = launch_sum_red(w + lay.red, nblk, 1, 1.0f, tail, st))) return rc;
+  }
+  {
+    ProfScope ps(PROF_GRAD, st);
+    if ((rc = launch_grad(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit, s->B, Ds, L, false, st))) return rc;
+    if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit, RC, w + lay.gradM, st))) return rc;
+  }
+  {
+    ProfScope ps(PROF_COMM, st);
+    if ((rc = allreduce_sum(s->comm, w + lay.gradM, RC + 4, st))) return rc;
+  }
   if (hess) {
     if ((rc = launch_grad(g.e_near, g.e_far, w + lay.phi2, w + lay.hres, w + lay.gpart, lay.gsplit, s->B, Ds, L, true, st))) return rc;
     if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit, RC, w + lay.hessM, st))) return rc;
     if ((rc = allreduce_sum(s->comm, w + lay.hessM, RC, st))) return rc;
   }
   float* scal = w + lay.scal;
+  ProfScope ps(PROF_SCALAR, st);
   if ((rc = launch_sum_red(tail, 1, 1, cost_norm(s), scal + TRMPS_S_COST0, st))) return rc;
   if ((rc = launch_grad_finish(w + lay.gradM, w + lay.bondM, hess ? w + lay.hessM : nullptr, w + lay.deltaM, RC, opt->reg,
                                2.f * opt->reg, w + lay.red, 296, st)))
@@ -219,13 +257,18 @@ static int do_bond_step(const trmps_sweep* s, const trmps_layout& lay, int site,
     ArmijoArgs aa;
     aa.f0 = w + lay.f0; aa.fdpart = w + lay.fpart; aa.nsplit = lay.nsplit; aa.fd = w + lay.fd; aa.labels = s->labels;
     aa.red = w + lay.red; aa.B = s->B; aa.L = L; aa.loss_kind = s->loss_kind; aa.lr = opt->lr;
+    ProfScope ps(PROF_SCALAR, st);
     if ((rc = launch_armijo(aa, st))) return rc;
     if ((rc = launch_sum_red(w + lay.red, (int)ceil_div64(s->B, 256), 19, cost_norm(s), scal + 8, st))) return rc;
     if ((rc = allreduce_sum(s->comm, scal + 8, 20, st))) return rc;
     if ((rc = launch_decide(scal, scal + 8, s->iwork, opt->lr, opt->armijo_coeff, st))) return rc;
     if ((rc = launch_apply_update(w + lay.bondM, delta, RC, w + lay.f0, w + lay.fd, s->B * L, scal, st))) return rc;
   }
-  if ((rc = svd_split(s, lay, g, opt, st))) return rc;
+  {
+    ProfScope ps(PROF_SVD, st);
+    if ((rc = svd_split(s, lay, g, opt, st))) return rc;
+  }
+  ProfScope ps_env(PROF_ENV, st);
   // environment advance (optimizer.py:187-190 / :132-135)
   const int64_t stride = s->B * (int64_t)Ds;
   const float* feat_site = s->feat + feat_site_offset(s->feature_map, s->B, site);
@@ -238,6 +281,7 @@ static int do_bond_step(const trmps_sweep* s, const trmps_layout& lay, int site,
 }
 
 static int do_init_env(const trmps_sweep* s, int loc, cudaStream_t st) {
+  ProfScope ps(PROF_ENV, st);
   const int Ds = s->Ds, N = s->N;
   const int64_t stride = s->B * (int64_t)Ds;
   const size_t slot = (size_t)2 * Ds * Ds;
@@ -315,6 +359,36 @@ using namespace trmps;
 
 // ================================================================================================= C ABI
 extern "C" int trmps_abi_version(void) { return TRMPS_ABI_VERSION; }
+extern "C" int64_t trmps_launch_count(void) { return (int64_t)g_launches; }
+
+extern "C" int trmps_profile_begin(int32_t max_records) {
+  if (max_records <= 0) { set_error("trmps_profile_begin: max_records must be positive"); return TRMPS_E_ARG; }
+  if (max_records > g_prof_cap) {
+    ProfRec* n = (ProfRec*)calloc((size_t)max_records, sizeof(ProfRec));
+    if (!n) { set_error("trmps_profile_begin: out of memory"); return TRMPS_E_ARG; }
+    if (g_prof) { memcpy(n, g_prof, sizeof(ProfRec) * g_prof_cap); free(g_prof); }
+    g_prof = n;
+    g_prof_cap = max_records;
+  }
+  g_prof_n = 0;
+  g_prof_on = true;
+  return TRMPS_OK;
+}
+
+extern "C" int trmps_profile_end(float* ms_per_cat, int32_t* count_per_cat, int32_t ncat) {
+  g_prof_on = false;
+  if (!ms_per_cat || !count_per_cat || ncat < PROF_NCAT) { set_error("trmps_profile_end: need %d categories", (int)PROF_NCAT); return TRMPS_E_ARG; }
+  for (int i = 0; i < ncat; ++i) { ms_per_cat[i] = 0.f; count_per_cat[i] = 0; }
+  for (int i = 0; i < g_prof_n; ++i) {
+    TRMPS_CUDA_OK(cudaEventSynchronize(g_prof[i].b));
+    float ms = 0.f;
+    TRMPS_CUDA_OK(cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b));
+    ms_per_cat[g_prof[i].cat] += ms;
+    count_per_cat[g_prof[i].cat] += 1;
+  }
+  g_prof_n = 0;
+  return TRMPS_OK;
+}
 extern "C" const char* trmps_last_error(void) { return g_err; }
 
 extern "C" int trmps_device_check(int device) {

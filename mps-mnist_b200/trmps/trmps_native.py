@@ -56,6 +56,9 @@ _SIGNATURES = {
     "trmps_abi_version": (C.c_int, []),
     "trmps_last_error": (C.c_char_p, []),
     "trmps_device_check": (C.c_int, [C.c_int]),
+    "trmps_launch_count": (C.c_int64, []),
+    "trmps_profile_begin": (C.c_int, [C.c_int32]),
+    "trmps_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]),
     "trmps_sweep_layout": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Layout)]),
     "trmps_predict_work_floats": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "trmps_feature_map": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -112,6 +115,26 @@ def check(rc, what):
 def require_gpu(device=0):
     """Fail loudly when the product path cannot run (no sm_100 device)."""
     check(load().trmps_device_check(int(device)), "trmps_device_check")
+
+
+PROF_CATEGORIES = ("env", "forward", "gradient", "svd", "merge", "scalar", "allreduce")
+
+
+def profile_begin(max_records=65536):
+    check(load().trmps_profile_begin(max_records), "trmps_profile_begin")
+
+
+def profile_end():
+    """-> {category: (milliseconds, number of timed regions)}"""
+    n = len(PROF_CATEGORIES)
+    ms = (C.c_float * n)()
+    cnt = (C.c_int32 * n)()
+    check(load().trmps_profile_end(ms, cnt, n), "trmps_profile_end")
+    return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(PROF_CATEGORIES)}
+
+
+def launch_count():
+    return int(load().trmps_launch_count())
 
 
 def sweep_layout(N, B, L, Ds, sm_count=148):

@@ -212,7 +212,7 @@ def test_split_matches_lapack(direction, D, max_size):
         assert dims[loc] == m
         ortho = np.einsum('mqi,mri->qr', node, node)
     assert rel(got, want) < RTOL
-    assert np.max(np.abs(ortho - np.eye(m))) < 1e-5        # a_j has orthonormal columns
+    assert np.max(np.abs(ortho - np.eye(m))) < 3e-5        # a_j has orthonormal columns
 
 
 # --------------------------------------------------------------------------------------------- full bond update / sweep
@@ -289,3 +289,38 @@ def test_optimizer_class_train_runs_and_learns(tmp_path):
     assert net.cost(f1, ds.training_data[1]) < c0
     again = MPS.from_file(str(tmp_path / "cfg"))
     assert rel(again.predict(ds.test_data[0]), net.predict(ds.test_data[0])) < 1e-6
+
+
+# --------------------------------------------------------------------------------------------- committed golden vectors
+import glob
+import os
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_cuda_path_reproduces_golden(path):
+    g = np.load(path)
+    N, B, L, ms, loc, lr, loss, upd, seed = g['cfg']
+    N, B, L, ms, loss, upd = int(N), int(B), int(L), int(ms), int(loss), int(upd)
+    pix, lab = g['pixels'], g['labels']
+    nodes, loc = o.initial_nodes(N, 2, L, loc=None if loc < 0 else int(loc))
+    st = make_state(N, B, L, ms, nodes, loc, pix, lab, fm=nat.FM_ONE_SQRT3, loss=loss)
+    w = st.weights_view()
+    assert rel(dev.predict(w, st.feat, nat.FM_ONE_SQRT3).cpu().numpy(), g['f_init']) < 1e-5
+    opt = dev.make_opt(lr=float(lr), max_size=ms, updates_per_step=upd)
+    st.init_env(loc)
+    sched = [(c, +1) for c in range(loc, N - 1)] + [(c, -1) for c in range(N - 1, 0, -1)] + [(c, +1) for c in range(0, loc)]
+    ms_seen, cost0 = [], []
+    for c, d in sched:
+        st.bond_step(c, d, opt)
+        iw, sc = st.iwork.cpu().numpy(), st.scalars().cpu().numpy()
+        ms_seen.append(int(iw[nat.I_M]))
+        cost0.append(float(sc[nat.S_COST0]))
+        sv = st.singular_values().cpu().numpy()[:6]
+        assert np.allclose(sv, g['s_top'][len(ms_seen) - 1], rtol=2e-3, atol=1e-5)
+    assert ms_seen == g['m'].tolist()                                  # kept bond dimensions: exact
+    assert np.allclose(cost0, g['cost0'][upd - 1::upd] if upd > 1 else g['cost0'], rtol=2e-3)
+    got = dev.predict(st.weights_view(), st.feat, nat.FM_ONE_SQRT3).cpu().numpy()
+    assert rel(got, g['f_final_f64']) < 10 * max(rel(g['f_final'], g['f_final_f64']), 1e-4)
+    assert np.mean(got.argmax(1) == g['f_final'].argmax(1)) >= 0.98

@@ -1,0 +1,135 @@
+"""CPU tests of the oracle itself: golden vectors, self-consistency (literal vs factored, fp32 vs fp64) and the
+invariants SURVEY.md section 8c lists."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import trmps_oracle as o
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def golden_cfg(g):
+    N, B, L, ms, loc, lr, loss, upd, seed = g['cfg']
+    return int(N), int(B), int(L), int(ms), (None if loc < 0 else int(loc)), float(lr), int(loss), int(upd), int(seed)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_oracle_reproduces_golden(path):
+    g = np.load(path)
+    N, B, L, ms, loc, lr, loss, upd, seed = golden_cfg(g)
+    pix, lab = o.synthetic_batch(N, B, L, seed=seed)
+    assert np.array_equal(pix, g['pixels']) and np.array_equal(lab, g['labels'])
+    phi = o.feature_map(pix, o.FM_ONE_SQRT3)
+    nodes, loc = o.initial_nodes(N, 2, L, loc=loc)
+    assert rel(o.predict(nodes, loc, phi, L), g['f_init']) < 1e-6
+    tr = o.Trace()
+    new = o.train_step(nodes, loc, phi, lab, lr, o.SweepParams(max_size=ms, updates_per_step=upd, loss_kind=loss), L, tr)
+    assert [t['trials'] for t in tr] == g['trials'].tolist()
+    assert [t['m'] for t in tr if 'm' in t] == g['m'].tolist()
+    assert np.allclose([t['cost0'] for t in tr], g['cost0'], rtol=1e-4)
+    assert rel(o.predict(new, loc, phi, L), g['f_final']) < 1e-3
+    assert rel(g['f_final'], g['f_final_f64']) < 1e-3           # fp32 error budget of the whole step
+
+
+def test_golden_files_present():
+    assert len(GOLDEN) >= 3
+
+
+def test_initial_mps_is_the_linear_model():
+    N, B, L = 20, 50, 10
+    rng = np.random.default_rng(0)
+    weight, bias = rng.normal(size=(N, 1, L)), rng.normal(size=(L,))
+    pix, _ = o.synthetic_batch(N, B, L, seed=1)
+    phi = o.feature_map(pix, o.FM_ONE_SQRT3)
+    for loc in (0, 7, N - 1):
+        nodes, _ = o.initial_nodes(N, 2, L, loc=loc, weight=weight, bias=bias)
+        lin = bias[None] + np.einsum('ntk,nkl->tl', phi[:, :, 1:], weight)
+        assert rel(o.predict(nodes, loc, phi, L), lin) < 1e-6
+
+
+def test_factored_forms_equal_literal():
+    N, B, L, D = 6, 40, 10, 12
+    pix, lab = o.synthetic_batch(N, B, L, seed=2)
+    phi = o.feature_map(pix, o.FM_COS_SIN)
+    nodes = o.random_full_bond_mps(N, 2, L, D, loc=2, seed=3)
+    C1s, C2s = o.setup_environments(nodes, 2, phi, L)
+    bond = np.einsum('lmij,njk->lmnik', nodes[2], nodes[3])
+    C = o.calculate_C(C1s[2], C2s[3], phi[2], phi[3])
+    p = o.SweepParams(max_size=D)
+    h, c, f = o.get_f_and_cost(bond, C, lab, p)
+    assert rel(o.forward_factored(bond, C1s[2], C2s[3], phi[2], phi[3]), f) < 1e-5
+    G = np.tensordot(lab - h, C, axes=([0], [0]))
+    assert rel(o.gradient_factored(lab - h, C1s[2], C2s[3], phi[2], phi[3]), G) < 1e-5
+    assert rel(o.chain_right_factored(C1s[2], phi[2], nodes[3][:, :D, :]), o.chain_right(C1s[2], phi[2], nodes[3][:, :D, :])) < 1e-5
+    assert rel(o.chain_left_factored(C2s[3], phi[3], nodes[3]), o.chain_left(C2s[3], phi[3], nodes[3])) < 1e-5
+
+
+def test_forward_is_linear_in_the_bond():
+    # f(B + lr*delta) = f(B) + lr*f(delta): what lets one forward on delta serve every Armijo trial
+    rng = np.random.default_rng(4)
+    B, L, D = 30, 10, 6
+    C = rng.normal(size=(B, 2, 2, D, D)).astype(np.float32)
+    b1 = rng.normal(size=(L, 2, 2, D, D)).astype(np.float32)
+    b2 = rng.normal(size=(L, 2, 2, D, D)).astype(np.float32)
+    f = lambda b: np.tensordot(C, b, axes=([1, 2, 3, 4], [1, 2, 3, 4]))
+    assert rel(f(b1 + np.float32(0.3) * b2), f(b1) + np.float32(0.3) * f(b2)) < 1e-5
+
+
+def test_split_properties():
+    rng = np.random.default_rng(5)
+    bond = rng.normal(size=(10, 2, 2, 9, 7)).astype(np.float32)
+    for max_size, expect in ((5, 5), (50, 18)):
+        a, a1 = o.bond_decomposition(bond, o.SweepParams(max_size=max_size, min_singular_value=1e-4))
+        m = a.shape[2]
+        assert m == expect
+        u = a.reshape(-1, m)
+        assert np.allclose(u.T @ u, np.eye(m), atol=1e-5)
+        flat = np.transpose(bond, (1, 3, 0, 2, 4)).reshape(18, -1)
+        uu, ss, vv = np.linalg.svd(flat.astype(np.float64), full_matrices=False)
+        trunc = (uu[:, :m] * ss[:m]) @ vv[:m]
+        assert rel(u @ a1.reshape(m, -1), trunc) < 1e-5
+    low = np.zeros_like(bond)      # rank-deficient bond -> clamped to min_size
+    a, a1 = o.bond_decomposition(low, o.SweepParams(max_size=30))
+    assert a.shape[2] == 3
+
+
+def test_armijo_halves_and_reverts():
+    rng = np.random.default_rng(6)
+    B, L, D = 50, 10, 4
+    C = rng.normal(size=(B, 2, 2, D, D)).astype(np.float32)
+    lab = np.eye(L, dtype=np.float32)[rng.integers(0, L, B)]
+    bond = (0.1 * rng.normal(size=(L, 2, 2, D, D))).astype(np.float32)
+    p = o.SweepParams(max_size=8)
+    tr = o.Trace()
+    new = o.update_bond(bond, C, lab, 1e3, p, tr)          # far too large a rate: needs several halvings
+    assert tr[0]['trials'] > 1 and tr[0]['cost1'] <= tr[0]['cost0']
+    tr2 = o.Trace()
+    kept = o.update_bond(bond, C, lab, 1e30, p, tr2)         # never acceptable within 19 trials -> bond kept
+    assert tr2[0]['trials'] == 19 and not tr2[0]['accepted'] and np.array_equal(kept, bond)
+
+
+def test_learning_rate_schedule_and_checkpoint_bytes():
+    assert abs(o.learning_rate(1.0, 0.99, 0) - 10.0) < 1e-9       # baseoptimizer.py:109
+    nodes, loc = o.initial_nodes(5, 2, 10)
+    raw = o.save_bytes(nodes, loc, 2, 10)
+    assert raw[0] == 1 and int.from_bytes(raw[1:3], 'big') == 5 and int.from_bytes(raw[3:5], 'big') == loc
+    back = o.load_bytes(raw)
+    assert all(np.array_equal(a, b) for a, b in zip(back['nodes'], nodes))
+    assert len(raw) == 9 + 2 * 5 + 4 * sum(n.size for n in nodes)
+
+
+def test_feature_maps():
+    x = np.array([[0.0, 0.5, 1.0]], dtype=np.float32)
+    assert np.allclose(o.feature_map(x, o.FM_ONE_SQRT3)[0], [[1, -np.sqrt(3)], [1, 0], [1, np.sqrt(3)]], atol=1e-6)
+    assert np.allclose(o.feature_map(x, o.FM_ONE_X)[0], [[1, 0], [1, 0.5], [1, 1]])
+    cs = o.feature_map(x, o.FM_COS_SIN)[0]
+    assert np.allclose(cs, [[1, 0], [np.sqrt(0.5), np.sqrt(0.5)], [0, 1]], atol=1e-6)
+    assert np.allclose((cs ** 2).sum(-1), 1, atol=1e-6)

@@ -55,7 +55,11 @@ def main():
     t = timed(lambda: st.bond_gradient(loc, +1, opt)); print("forward+loss+gradient         min %.3f ms  med %.3f ms" % t)
     st.bond_merge(loc, +1)
     t = timed(lambda: (st.bond_merge(loc, +1), st.bond_split(loc, +1, opt), st.set_nodes(nodes, loc))[0], reps=3, warm=1)
-    print("merge+split(+reset)           min %.3f ms  med %.3f ms  sweeps=%d m=%d" % (*t, int(st.iwork.cpu()[nat.I_SVD_SWEEPS]), int(st.iwork.cpu()[nat.I_M])))
+    iw = st.iwork.cpu().numpy()
+    print("merge+split(+reset)           min %.3f ms  med %.3f ms  sweeps=%d m=%d" % (*t, iw[nat.I_SVD_SWEEPS], iw[nat.I_M]))
+    ns = int(iw[nat.I_SVD_SWEEPS])
+    print("  CTAs that rotated per sweep:", iw[8:8 + ns].tolist())
+    print("  max rel off-diagonal per sweep:", ["%.1e" % x for x in iw[40:40 + ns].view(np.float32).tolist()])
 
     def full():
         st.set_nodes(nodes, loc)
