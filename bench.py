@@ -53,8 +53,13 @@ def synthetic_pixels(N, B, L, seed):
     return pixels, labels
 
 
+COS_SIN_SCALE = 0.7893698     # exp(-E[log(cos(pi x/2) + sin(pi x/2))]), x ~ U[0,1): keeps the chain product O(1)
+
+
 def full_bond_mps(N, d, L, D, loc, seed=1):
-    """Near-identity site tensors + N(0, (0.1/sqrt(D))^2) noise, all internal bonds = D."""
+    """Full-bond random MPS for fixed-D runs: every internal bond = D, outer bonds 2L.  Each site
+    tensor is COS_SIN_SCALE * identity on BOTH feature components plus N(0, (0.1/sqrt(D))^2) noise, so that with the
+    [cos, sin] feature map the 196-site product neither under- nor overflows and the logits are O(1)."""
     rng = np.random.default_rng(seed)
     noise = 0.1 / np.sqrt(D)
     dims = [2 * L] + [D] * (N - 1) + [2 * L]
@@ -63,9 +68,9 @@ def full_bond_mps(N, d, L, D, loc, seed=1):
         dl, dr = dims[i], dims[i + 1]
         base = np.zeros((d, dl, dr))
         k = min(dl, dr)
-        base[0, :k, :k] = np.eye(k)
+        base[:, :k, :k] = np.eye(k) * COS_SIN_SCALE
         if i == loc:
-            node = 0.5 * base[None] + rng.normal(0.0, noise, size=(L, d, dl, dr))
+            node = base[None] + rng.normal(0.0, noise, size=(L, d, dl, dr))
         else:
             node = base + rng.normal(0.0, noise, size=(d, dl, dr))
         nodes.append(node.astype(np.float32))

@@ -30,7 +30,7 @@ constexpr int SVD_WARPS = SVD_THREADS / 32;
 
 struct SvdArgs {
   float* M; float* Ut; int R, Cc, Ds; const int32_t* d_near; int32_t* iscal; int32_t* rowmap; float* norms;
-  float tol; int max_sweeps;
+  float tol; int max_sweeps; float* dbg;   // dbg: 8 floats, phase cycle counters of CTA 0 (load, gram, rotate, replay, store, grid sync)
 };
 
 __device__ __forceinline__ int compact_to_row(int p, int dn, int Ds) { return (p / dn) * Ds + (p % dn); }
@@ -83,26 +83,15 @@ __global__ void svd_init_ut_kernel(SvdArgs a) {
   if (p < Ra) a.Ut[(size_t)p * a.R + a.rowmap[p]] = 1.f;
 }
 
-// round-robin pairing of n players (n even): partner pair #j in step s
+// round-robin pairing of n players (n even): pair #j in step s
 __host__ __device__ constexpr int rr_first(int n, int s, int j) { return j == 0 ? n - 1 : (s + j) % (n - 1); }
 __host__ __device__ constexpr int rr_second(int n, int s, int j) { return j == 0 ? s : (s + n - 1 - j) % (n - 1); }
 
-// local row indices of pair p in a step.  kind 0: cross pairs (row p of block I with row (p+s)%BLK of block J);
-// kind 1: pairs inside the blocks (first BLK/2 pairs in block I, the rest in block J)
-template <int BLK>
-__host__ __device__ constexpr int pair_x(int kind, int s, int p) {
-  return kind == 0 ? p : (p < BLK / 2 ? rr_first(BLK, s, p) : BLK + rr_first(BLK, s, p - BLK / 2));
-}
-template <int BLK>
-__host__ __device__ constexpr int pair_y(int kind, int s, int p) {
-  return kind == 0 ? BLK + (p + s) % BLK : (p < BLK / 2 ? rr_second(BLK, s, p) : BLK + rr_second(BLK, s, p - BLK / 2));
-}
-
 // per-warp partial sums of K per-thread values -> part[warp][k]  (first stage of a deterministic block reduction).
 // Transposing butterfly: each exchange halves the number of live values, so K values cost K-1+log2(32/K)
-// shuffles instead of 5K.  K must be a power of two <= 32.
+// shuffles instead of 5K.  K must be a power of two <= 32.  No barrier inside.
 template <int K>
-__device__ __forceinline__ void warp_partials(float (&x)[K], float (*part)[16], int lane, int warp) {
+__device__ __forceinline__ void warp_partials(float (&x)[K], float (*part)[32], int lane, int warp) {
   int idx = 0;
   int o = 16;
 #pragma unroll
@@ -117,21 +106,39 @@ __device__ __forceinline__ void warp_partials(float (&x)[K], float (*part)[16], 
     if (hi) idx += n / 2;
     o >>= 1;
   }
-  const int rest = 2 * o - 1;   // lanes that differ only in these bits hold partials of the same value
+  const int rest = o > 0 ? 2 * o - 1 : 0;   // lanes that differ only in these bits hold partials of the same value
   for (; o > 0; o >>= 1) x[0] += __shfl_xor_sync(0xffffffffu, x[0], o);
   if ((lane & rest) == 0) part[warp][idx] = x[0];
-  __syncthreads();
 }
 
+template <int N, typename F>
+__device__ __forceinline__ void replay_all_steps(F&& f) {
+  if constexpr (N > 0) {
+    replay_all_steps<N - 1>(f);
+    f(std::integral_constant<int, N - 1>{});
+  }
+}
+
+// Block one-sided Jacobi.  Per round a CTA holds NR rows (two blocks) in registers and
+//   1. forms their NR x NR Gram matrix (per-thread partials, deterministic block reduction),
+//   2. runs the plane rotations of the round on the small Gram in shared memory (exactly the rotations
+//      Hestenes' method would apply to the long rows, since a rotation's angle only needs the three
+//      inner products), recording (s, tau) of every rotation,
+//   3. replays the recorded rotations on the register-resident rows and on the rows of U^T, with no
+//      synchronisation in between, in Rutishauser's form (norm-preserving in fp32 even when cos rounds to 1,
+//      which would otherwise inflate every row by +t^2 per rotation).
 template <int NR, int SLOTS>
 __global__ void __launch_bounds__(SVD_THREADS) svd_jacobi_kernel(SvdArgs a) {
   cg::grid_group grid = cg::this_grid();
-  constexpr int BLK = NR / 2, NP = BLK;
+  constexpr int BLK = NR / 2, NP = NR / 2, NGRP = NR * NR / 16, LD = NR + 1;
   extern __shared__ __align__(16) float uts[];   // [NR][R]
-  __shared__ float part[SVD_WARPS][16];
-  __shared__ float nrm[NR];
-  __shared__ float rot_c[NP], rot_s[NP];
+  __shared__ float part[2][SVD_WARPS][32];
+  __shared__ float Gs[2][NR][LD];
+  __shared__ float rot_c[NR], rot_b[NR];      // per ROW of the current step: self coefficient c, partner coefficient (+-s)
+  __shared__ float rec_s[NR - 1][NP], rec_tau[NR - 1][NP];   // recorded rotations of the round: (s, tau) per (step, pair)
+  __shared__ int partner[NR];
   __shared__ int srow[NR];
+  __shared__ int smrow[NR];   // padded row index in M of each local row
   __shared__ int sflag;
   __shared__ float smax;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -145,6 +152,9 @@ __global__ void __launch_bounds__(SVD_THREADS) svd_jacobi_kernel(SvdArgs a) {
   const bool active = q < nbe / 2;
   int sweeps_used = 0;
   float v[NR][SLOTS];
+  const bool timer = blockIdx.x == 0 && tid == 0;
+  long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = timer ? clock64() : 0;
+  auto tick = [&](int k) { if (timer) { long long now = clock64(); tacc[k] += now - tprev; tprev = now; } };
 
   for (int sweep = 0; sweep < a.max_sweeps; ++sweep) {
     for (int r = 0; r < rounds; ++r) {
@@ -155,15 +165,17 @@ __global__ void __launch_bounds__(SVD_THREADS) svd_jacobi_kernel(SvdArgs a) {
         if (tid < NR) {
           int blk = tid < BLK ? bi : bj;
           int p = blk * BLK + (tid % BLK);
-          srow[tid] = (blk < nb && p < Ra) ? p : -1;
+          const bool ok = blk < nb && p < Ra;
+          srow[tid] = ok ? p : -1;
+          smrow[tid] = ok ? __ldcg(&a.rowmap[p]) : 0;
         }
         if (tid == 0) { sflag = 0; smax = 0.f; }
         __syncthreads();
-        // load the NR rows: thread owns columns tid + SVD_THREADS * slot
+        // ---- load the NR rows: thread owns columns tid + SVD_THREADS * slot
 #pragma unroll
         for (int x = 0; x < NR; ++x) {
           const int p = srow[x];
-          const float* src = p >= 0 ? a.M + (size_t)__ldcg(&a.rowmap[p]) * Cc : nullptr;
+          const float* src = p >= 0 ? a.M + (size_t)smrow[x] * Cc : nullptr;
 #pragma unroll
           for (int sl = 0; sl < SLOTS; ++sl) {
             int c = tid + SVD_THREADS * sl;
@@ -171,137 +183,131 @@ __global__ void __launch_bounds__(SVD_THREADS) svd_jacobi_kernel(SvdArgs a) {
           }
           if (tid < R) uts[x * R + tid] = p >= 0 ? __ldcg(a.Ut + (size_t)p * R + tid) : 0.f;
         }
-        // refresh the squared norms from the data
-        {
-          float n2[NR];
+        tick(0);
+        // ---- Gram matrix (upper triangle), 16 entries (16/NR rows) per block reduction
 #pragma unroll
-          for (int x = 0; x < NR; ++x) {
+        for (int grp = 0; grp < NGRP; ++grp) {
+          float pg[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int x = grp * (16 / NR) + k / NR, y = k % NR;
             float s = 0.f;
+            if (y >= x) {
 #pragma unroll
-            for (int sl = 0; sl < SLOTS; ++sl) s = fmaf(v[x][sl], v[x][sl], s);
-            n2[x] = s;
+              for (int sl = 0; sl < SLOTS; ++sl) s = fmaf(v[x][sl], v[y][sl], s);
+            }
+            pg[k] = s;
           }
-          warp_partials<NR>(n2, part, lane, warp);
-          if (tid < NR * SVD_WARPS) {
-            int j = tid / SVD_WARPS, w = tid % SVD_WARPS;
-            float s = part[w][j];
+          warp_partials<16>(pg, part[grp & 1], lane, warp);
+          __syncthreads();
+          if (tid < 16 * SVD_WARPS) {
+            const int j = tid / SVD_WARPS, w = tid % SVD_WARPS;   // 16 values x 16 warps
+            float s = part[grp & 1][w][j];
 #pragma unroll
             for (int o = SVD_WARPS / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (w == 0) nrm[j] = s;
+            const int x = grp * (16 / NR) + j / NR, y = j % NR;
+            if (w == 0 && y >= x) { Gs[0][x][y] = s; Gs[0][y][x] = s; }
+          }
+        }
+        __syncthreads();
+        tick(1);
+        // ---- rotations of this round on the small Gram
+        const int nsteps = r == 0 ? NR - 1 : BLK;    // first round of a sweep: all pairs of the NR rows; else cross-block pairs
+        int cur = 0;
+        for (int step = 0; step < nsteps; ++step) {
+          if (tid < NP) {
+            int x, y;
+            if (r == 0) { x = rr_first(NR, step, tid); y = rr_second(NR, step, tid); }
+            else { x = tid; y = BLK + (tid + step) % BLK; }
+            const float al = Gs[cur][x][x], be = Gs[cur][y][y], ga = Gs[cur][x][y];
+            float c = 1.f, s = 0.f, tau = 0.f;
+            const float big = fmaxf(al, be), small = fminf(al, be);
+            if (srow[x] >= 0 && srow[y] >= 0 && small > 1e-30f && small > 1e-24f * big) {
+              const float relg = fabsf(ga) / (sqrtf(al) * sqrtf(be));
+              if (relg > a.tol) {
+                const float zeta = (be - al) / (2.f * ga);
+                const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
+                c = 1.f / sqrtf(fmaf(t, t, 1.f));
+                s = c * t;
+                tau = s / (1.f + c);
+                sflag = 1;
+                atomicMax(reinterpret_cast<int*>(&smax), __float_as_int(relg));   // relg >= 0: int order == float order
+              }
+            }
+            // x' = c x - s y ; y' = s x + c y
+            partner[x] = y; rot_c[x] = c; rot_b[x] = -s;
+            partner[y] = x; rot_c[y] = c; rot_b[y] = s;
+            rec_s[step][tid] = s;
+            rec_tau[step][tid] = tau;
           }
           __syncthreads();
+          if (tid < NR * NR) {
+            const int i = tid / NR, j = tid % NR, pi = partner[i], pj = partner[j];
+            const float ai = rot_c[i], bi_ = rot_b[i], aj = rot_c[j], bj_ = rot_b[j];
+            float g = ai * aj * Gs[cur][i][j];
+            g = fmaf(ai * bj_, Gs[cur][i][pj], g);
+            g = fmaf(bi_ * aj, Gs[cur][pi][j], g);
+            g = fmaf(bi_ * bj_, Gs[cur][pi][pj], g);
+            Gs[cur ^ 1][i][j] = g;
+          }
+          __syncthreads();
+          cur ^= 1;
         }
-
-        auto do_steps = [&](auto kind_tag, int nsteps) {
-          constexpr int KIND = decltype(kind_tag)::value;
-#pragma unroll 1
-          for (int step = 0; step < nsteps; ++step) {
-            float g[NP];
-            // (the row indices must be compile-time for the register file: switch over the step)
-            auto dots = [&](auto step_tag) {
-              constexpr int S = decltype(step_tag)::value;
+        tick(2);
+        // ---- replay the recorded rotations on the register-resident rows and on the rows of U^T, in Rutishauser's
+        //      form x' = x - s (y + tau x), y' = y + s (x - tau y)  (norm-preserving even when cos rounds to 1)
+        if (sflag) {
+          auto replay = [&](auto kind_tag, auto step_tag) {
+            constexpr int ALL = decltype(kind_tag)::value, S = decltype(step_tag)::value;
 #pragma unroll
-              for (int p = 0; p < NP; ++p) {
-                const int x = pair_x<BLK>(KIND, S, p), y = pair_y<BLK>(KIND, S, p);
-                float s = 0.f;
+            for (int p = 0; p < NP; ++p) {
+              const int x = ALL ? rr_first(NR, S, p) : p;
+              const int y = ALL ? rr_second(NR, S, p) : BLK + (p + S) % BLK;
+              const float sn = rec_s[S][p], tau = rec_tau[S][p];
+              if (sn != 0.f) {
 #pragma unroll
-                for (int sl = 0; sl < SLOTS; ++sl) s = fmaf(v[x][sl], v[y][sl], s);
-                g[p] = s;
-              }
-            };
-            auto apply = [&](auto step_tag) {
-              constexpr int S = decltype(step_tag)::value;
-#pragma unroll
-              for (int p = 0; p < NP; ++p) {
-                const int x = pair_x<BLK>(KIND, S, p), y = pair_y<BLK>(KIND, S, p);
-                // Rutishauser's form x' = x - s (y + tau x), y' = y + s (x - tau y), tau = s / (1 + c): the
-                // second-order term keeps the rotation norm-preserving even when c rounds to 1 in fp32
-                const float tau = rot_c[p], s = rot_s[p];
-                if (s != 0.f) {
-#pragma unroll
-                  for (int sl = 0; sl < SLOTS; ++sl) {
-                    float u = v[x][sl], w = v[y][sl];
-                    v[x][sl] = fmaf(-s, fmaf(tau, u, w), u);
-                    v[y][sl] = fmaf(s, fmaf(-tau, w, u), w);
-                  }
-                  if (tid < R) {
-                    float u = uts[x * R + tid], w = uts[y * R + tid];
-                    uts[x * R + tid] = fmaf(-s, fmaf(tau, u, w), u);
-                    uts[y * R + tid] = fmaf(s, fmaf(-tau, w, u), w);
-                  }
+                for (int sl = 0; sl < SLOTS; ++sl) {
+                  const float u = v[x][sl], w = v[y][sl];
+                  v[x][sl] = fmaf(-sn, fmaf(tau, u, w), u);
+                  v[y][sl] = fmaf(sn, fmaf(-tau, w, u), w);
+                }
+                if (tid < R) {
+                  const float u = uts[x * R + tid], w = uts[y * R + tid];
+                  uts[x * R + tid] = fmaf(-sn, fmaf(tau, u, w), u);
+                  uts[y * R + tid] = fmaf(sn, fmaf(-tau, w, u), w);
                 }
               }
-            };
-            auto dispatch = [&](auto&& fn) {
-              switch (step) {
-                case 0: fn(std::integral_constant<int, 0>{}); break;
-                case 1: fn(std::integral_constant<int, 1>{}); break;
-                case 2: if constexpr (BLK > 2) fn(std::integral_constant<int, 2>{}); break;
-                case 3: if constexpr (BLK > 2) fn(std::integral_constant<int, 3>{}); break;
-                case 4: if constexpr (BLK > 4) fn(std::integral_constant<int, 4>{}); break;
-                case 5: if constexpr (BLK > 4) fn(std::integral_constant<int, 5>{}); break;
-                case 6: if constexpr (BLK > 4) fn(std::integral_constant<int, 6>{}); break;
-                case 7: if constexpr (BLK > 4) fn(std::integral_constant<int, 7>{}); break;
-                default: break;
-              }
-            };
-            dispatch(dots);
-            warp_partials<NP>(g, part, lane, warp);
-            if (tid < NP * SVD_WARPS) {
-              const int j = tid / SVD_WARPS, w = tid % SVD_WARPS;
-              float ga = part[w][j];
-#pragma unroll
-              for (int o = SVD_WARPS / 2; o > 0; o >>= 1) ga += __shfl_xor_sync(0xffffffffu, ga, o);
-              if (w == 0) {
-                const int x = pair_x<BLK>(KIND, step, j), y = pair_y<BLK>(KIND, step, j);
-                const float al = nrm[x], be = nrm[y];
-                float tau = 0.f, s = 0.f;
-                const float big = fmaxf(al, be), small = fminf(al, be);
-                if (small > 1e-30f && small > 1e-24f * big) {
-                  const float relg = fabsf(ga) / (sqrtf(al) * sqrtf(be));
-                  if (relg > a.tol) {
-                    const float zeta = (be - al) / (2.f * ga);
-                    const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
-                    const float c = 1.f / sqrtf(fmaf(t, t, 1.f));
-                    s = c * t;
-                    tau = s / (1.f + c);
-                    nrm[x] = al - t * ga;
-                    nrm[y] = be + t * ga;
-                    sflag = 1;
-                    atomicMax(reinterpret_cast<int*>(&smax), __float_as_int(relg));   // relg >= 0: int order == float order
-                  }
-                }
-                rot_c[j] = tau;
-                rot_s[j] = s;
-              }
             }
-            __syncthreads();
-            dispatch(apply);
+          };
+          if (r == 0) {
+            replay_all_steps<NR - 1>([&](auto st) { replay(std::integral_constant<int, 1>{}, st); });
+          } else {
+            replay_all_steps<BLK>([&](auto st) { replay(std::integral_constant<int, 0>{}, st); });
           }
-        };
-        if (r == 0) do_steps(std::integral_constant<int, 1>{}, BLK - 1);   // pairs inside each block: once per sweep
-        do_steps(std::integral_constant<int, 0>{}, BLK);                     // cross-block pairs
-        __syncthreads();
-        // write back
+          tick(3);
+          // ---- write back
 #pragma unroll
-        for (int x = 0; x < NR; ++x) {
-          const int p = srow[x];
-          if (p >= 0) {
-            float* dst = a.M + (size_t)__ldcg(&a.rowmap[p]) * Cc;
+          for (int x = 0; x < NR; ++x) {
+            const int p = srow[x];
+            if (p >= 0) {
+              float* dst = a.M + (size_t)smrow[x] * Cc;
 #pragma unroll
-            for (int sl = 0; sl < SLOTS; ++sl) {
-              int c = tid + SVD_THREADS * sl;
-              if (c < Cc) __stcg(dst + c, v[x][sl]);
+              for (int sl = 0; sl < SLOTS; ++sl) {
+                int c = tid + SVD_THREADS * sl;
+                if (c < Cc) __stcg(dst + c, v[x][sl]);
+              }
+              if (tid < R) __stcg(a.Ut + (size_t)p * R + tid, uts[x * R + tid]);
             }
-            if (tid < R) __stcg(a.Ut + (size_t)p * R + tid, uts[x * R + tid]);
+          }
+          if (tid == 0) {
+            atomicAdd(&a.iscal[TRMPS_I_SVD_ROT + sweep], 1);
+            atomicMax(&a.iscal[TRMPS_I_SVD_ROT + 32 + (sweep & 31)], __float_as_int(smax));
           }
         }
-        if (tid == 0 && sflag) {
-          atomicAdd(&a.iscal[TRMPS_I_SVD_ROT + sweep], 1);
-          atomicMax(&a.iscal[TRMPS_I_SVD_ROT + 32 + (sweep & 31)], __float_as_int(smax));
-        }
+        tick(4);
       }
       grid.sync();
+      tick(5);
     }
     sweeps_used = sweep + 1;
     const int nrot = __ldcg(&a.iscal[TRMPS_I_SVD_ROT + sweep]);
@@ -309,7 +315,307 @@ __global__ void __launch_bounds__(SVD_THREADS) svd_jacobi_kernel(SvdArgs a) {
     // quadratic convergence: a sweep whose largest relative off-diagonal was eps leaves O(eps^2) behind
     if (nrot == 0 || worst < 2e-4f) break;
   }
-  if (blockIdx.x == 0 && tid == 0) a.iscal[TRMPS_I_SVD_SWEEPS] = sweeps_used;
+  if (blockIdx.x == 0 && tid == 0) {
+    a.iscal[TRMPS_I_SVD_SWEEPS] = sweeps_used;
+    if (a.dbg) for (int k = 0; k < 6; ++k) a.dbg[k] = (float)tacc[k];
+  }
+}
+
+// =====================================================================================================
+// Cluster version (the one normally used): CL_SIZE CTAs form a thread-block cluster per row-block pair; each
+// CTA owns a contiguous slice of the columns (and of the columns of U^T), so a round's load, Gram partials,
+// rotation replay and store are spread over 8x more SMs.  The 16 x 16 Gram partials of the 8 CTAs are summed
+// through distributed shared memory in a fixed order, so all CTAs of a cluster (and all ranks of a data-parallel
+// job) hold bit-identical Gram matrices and take identical rotation decisions.  Rounds are chained by
+// per-(block, slice) release/acquire flags in global memory instead of a grid barrier: CTA k of a cluster only
+// waits for the CTAs with the same rank k that held its two blocks in the previous round.  One grid barrier per
+// sweep decides convergence.
+constexpr int CL_THREADS = 256, CL_WARPS = CL_THREADS / 32, CL_SIZE = 8, CL_NR = 16, CL_NG = CL_NR * (CL_NR + 1) / 2;
+constexpr int CL_MAXU = 64;   // columns of U^T per CTA (R <= 512)
+
+struct SvdClArgs {
+  SvdArgs a; int cols_per_cta; int ucols_per_cta; int32_t* flags;   // flags: [blocks][CL_SIZE] rounds completed
+};
+
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// partner / role of `row` in step `step`; all = 1: round-robin over the 16 rows, else cross-block pairs
+__device__ __forceinline__ void pair_of_row(int all, int step, int row, int& x, int& y, int& pidx) {
+  constexpr int NR = CL_NR, BLK = CL_NR / 2;
+  if (!all) {
+    if (row < BLK) { x = row; y = BLK + (row + step) % BLK; pidx = row; }
+    else { y = row; x = (row - BLK - step % BLK + BLK) % BLK; pidx = x; }
+    return;
+  }
+  if (row == NR - 1) { x = NR - 1; y = step; pidx = 0; return; }
+  if (row == step) { x = NR - 1; y = step; pidx = 0; return; }
+  const int j = (row - step + (NR - 1)) % (NR - 1);     // 1 .. NR-2
+  if (j <= (NR - 2) / 2) { pidx = j; x = row; y = (step + (NR - 1) - j) % (NR - 1); }
+  else { pidx = (NR - 1) - j; y = row; x = (step + pidx) % (NR - 1); }
+}
+
+// rotation that annihilates the (x,y) entry of a 2x2 Gram [[al, ga],[ga, be]]: x' = c x - s y, y' = s x + c y
+__device__ __forceinline__ bool rotation_params(float al, float be, float ga, float tol, float& c, float& s, float& tau, float& relg) {
+  c = 1.f; s = 0.f; tau = 0.f; relg = 0.f;
+  const float big = fmaxf(al, be), small = fminf(al, be);
+  if (!(small > 1e-30f && small > 1e-24f * big)) return false;
+  relg = fabsf(ga) * rsqrtf(al) * rsqrtf(be);
+  if (!(relg > tol)) return false;
+  const float zeta = __fdividef(be - al, 2.f * ga);
+  const float h2 = fmaf(zeta, zeta, 1.f);
+  const float t = __fdividef(copysignf(1.f, zeta), fabsf(zeta) + h2 * rsqrtf(h2));
+  c = rsqrtf(fmaf(t, t, 1.f));
+  s = c * t;
+  tau = __fdividef(s, 1.f + c);
+  return true;
+}
+
+template <int SLOTS>
+__global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArgs ca) {
+  cg::grid_group grid = cg::this_grid();
+  cg::cluster_group cluster = cg::this_cluster();
+  constexpr int NR = CL_NR, BLK = NR / 2, NP = NR / 2, NG = CL_NG, LD = NR + 1, NCH = (NG + 31) / 32;
+  const SvdArgs& a = ca.a;
+  __shared__ float uts[NR][CL_MAXU];
+  __shared__ float part[CL_WARPS][NCH * 32];
+  __shared__ float cta_g[2][NG];
+  __shared__ float Gs[2][NR][LD];
+  __shared__ float rec_s[NR - 1][NP], rec_tau[NR - 1][NP];
+  __shared__ int srow[NR], smrow[NR];
+  __shared__ int sflag;
+  __shared__ float smax;
+  __shared__ unsigned char tab_partner[2][NR - 1][NR], tab_first[2][NR - 1][NR], tab_pidx[2][NR - 1][NR];
+  __shared__ unsigned char tab_x[2][NR - 1][NP], tab_y[2][NR - 1][NP];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < 2 * (NR - 1) * NR; e += CL_THREADS) {
+    const int row = e % NR, step = (e / NR) % (NR - 1), all_ = e / (NR * (NR - 1));
+    int x, y, pidx;
+    pair_of_row(all_, step, row, x, y, pidx);
+    tab_partner[all_][step][row] = (unsigned char)(row == x ? y : x);
+    tab_first[all_][step][row] = (unsigned char)(row == x);
+    tab_pidx[all_][step][row] = (unsigned char)pidx;
+    if (row == x) { tab_x[all_][step][pidx] = (unsigned char)x; tab_y[all_][step][pidx] = (unsigned char)y; }
+  }
+  __syncthreads();
+  const int crank = (int)cluster.block_rank();
+  const int q = blockIdx.x / CL_SIZE;
+  const int Cc = a.Cc, R = a.R;
+  const int c0 = crank * ca.cols_per_cta, c1 = min(Cc, c0 + ca.cols_per_cta);
+  const int u0 = crank * ca.ucols_per_cta, ucnt = max(0, min(R, u0 + ca.ucols_per_cta) - u0);
+  const int dn = *a.d_near, Ra = 2 * dn;
+  const int nb = (Ra + BLK - 1) / BLK;
+  int nbe = nb + (nb & 1);
+  if (nbe < 2) nbe = 2;
+  const int rounds = nbe - 1;
+  const bool active = q < nbe / 2;
+  int sweeps_used = 0, ground = 0;     // ground: global round counter (flags hold the number of completed rounds)
+  float v[NR][SLOTS];
+  const bool timer = blockIdx.x == 0 && tid == 0;
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = timer ? clock64() : 0;
+  auto tick = [&](int k) { if (timer) { long long now = clock64(); tacc[k] += now - tprev; tprev = now; } };
+
+  for (int sweep = 0; sweep < a.max_sweeps; ++sweep) {
+    for (int r = 0; r < rounds; ++r, ++ground) {
+      if (!active) continue;
+      int bi, bj;
+      if (q == 0) { bi = nbe - 1; bj = r; }
+      else { bi = (r + q) % (nbe - 1); bj = (r + nbe - 1 - q) % (nbe - 1); }
+      if (tid < NR) {
+        const int blk = tid < BLK ? bi : bj;
+        const int p = blk * BLK + (tid % BLK);
+        const bool ok = blk < nb && p < Ra;
+        srow[tid] = ok ? p : -1;
+        smrow[tid] = ok ? __ldcg(&a.rowmap[p]) : 0;
+      }
+      if (tid == 0) {
+        sflag = 0; smax = 0.f;
+        // wait until the previous holders of my two blocks (same column slice) have stored them
+        if (bi < nb) while (ld_volatile(&ca.flags[bi * CL_SIZE + crank]) < ground) { }
+        if (bj < nb) while (ld_volatile(&ca.flags[bj * CL_SIZE + crank]) < ground) { }
+        __threadfence();
+      }
+      __syncthreads();
+      tick(6);
+      // ---- load my column slice of the NR rows (registers) and of their U^T rows (shared)
+#pragma unroll
+      for (int x = 0; x < NR; ++x) {
+        const int p = srow[x];
+        const float* src = a.M + (size_t)smrow[x] * Cc;
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) {
+          const int c = c0 + tid + CL_THREADS * sl;
+          v[x][sl] = (p >= 0 && c < c1) ? __ldcg(src + c) : 0.f;
+        }
+        if (tid < ucnt) uts[x][tid] = p >= 0 ? __ldcg(a.Ut + (size_t)p * R + u0 + tid) : 0.f;
+      }
+      tick(0);
+      // ---- Gram partials of my slice (upper triangle, row-major), reduced over the CTA
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        float pg[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) pg[k] = 0.f;
+#pragma unroll
+        for (int x = 0; x < NR; ++x) {
+#pragma unroll
+          for (int y = x; y < NR; ++y) {
+            const int idx = x * NR - x * (x - 1) / 2 + (y - x);
+            if (idx / 32 == ch) {
+              float s = 0.f;
+#pragma unroll
+              for (int sl = 0; sl < SLOTS; ++sl) s = fmaf(v[x][sl], v[y][sl], s);
+              pg[idx % 32] = s;
+            }
+          }
+        }
+        warp_partials<32>(pg, reinterpret_cast<float(*)[32]>(&part[0][0]), lane, warp * NCH + ch);
+      }
+      __syncthreads();
+      const int par = ground & 1;
+      if (tid < NG) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < CL_WARPS; ++w) s += part[w][tid];
+        cta_g[par][tid] = s;
+      }
+      cluster.sync();
+      if (tid < NG) {
+        float s = 0.f;
+#pragma unroll
+        for (int rk = 0; rk < CL_SIZE; ++rk) s += cluster.map_shared_rank(&cta_g[par][0], rk)[tid];
+        int x = 0, rem = tid;
+        while (rem >= NR - x) { rem -= NR - x; ++x; }
+        const int y = x + rem;
+        Gs[0][x][y] = s;
+        Gs[0][y][x] = s;
+      }
+      __syncthreads();
+      tick(1);
+      // ---- rotations of this round on the small Gram.  Every warp recomputes the 8 rotations of the step (lane & 7),
+      //      thread (i, j) fetches the two it needs by shuffle and updates G[i][j]: one barrier per step.
+      const int all = r == 0 ? 1 : 0;
+      const int nsteps = all ? NR - 1 : BLK;
+      int cur = 0;
+      {
+        const int i = tid / NR, j = tid % NR, pl = lane & 7;
+        float worst_rel = 0.f;
+        for (int step = 0; step < nsteps; ++step) {
+          const int px = tab_x[all][step][pl], py = tab_y[all][step][pl];
+          float c, sn, tau, relg;
+          bool rot = rotation_params(Gs[cur][px][px], Gs[cur][py][py], Gs[cur][px][py], a.tol, c, sn, tau, relg);
+          if (!(srow[px] >= 0 && srow[py] >= 0)) { rot = false; c = 1.f; sn = 0.f; tau = 0.f; }
+          const int qi = tab_pidx[all][step][i], qj = tab_pidx[all][step][j];
+          const float ci = __shfl_sync(0xffffffffu, c, qi), si = __shfl_sync(0xffffffffu, sn, qi);
+          const float cj = __shfl_sync(0xffffffffu, c, qj), sj = __shfl_sync(0xffffffffu, sn, qj);
+          const int opi = tab_partner[all][step][i], opj = tab_partner[all][step][j];
+          const float bi_ = tab_first[all][step][i] ? -si : si, bj_ = tab_first[all][step][j] ? -sj : sj;
+          float g = ci * cj * Gs[cur][i][j];
+          g = fmaf(ci * bj_, Gs[cur][i][opj], g);
+          g = fmaf(bi_ * cj, Gs[cur][opi][j], g);
+          g = fmaf(bi_ * bj_, Gs[cur][opi][opj], g);
+          Gs[cur ^ 1][i][j] = g;
+          if (tid < NP) {                 // warp 0, lanes 0..7: one lane per pair records the rotation
+            rec_s[step][tid] = sn;
+            rec_tau[step][tid] = tau;
+            if (rot) {
+              sflag = 1;
+              worst_rel = fmaxf(worst_rel, relg);
+            }
+          }
+          __syncthreads();
+          cur ^= 1;
+        }
+        if (tid < NP && worst_rel > 0.f) atomicMax(reinterpret_cast<int*>(&smax), __float_as_int(worst_rel));
+        __syncthreads();
+      }
+      tick(2);
+      // ---- replay the recorded rotations on my slice of the rows and of U^T (Rutishauser form), then store
+      if (sflag) {
+        auto replay = [&](auto kind_tag, auto step_tag) {
+          constexpr int ALL = decltype(kind_tag)::value, S = decltype(step_tag)::value;
+          float sn[NP], ta[NP];
+#pragma unroll
+          for (int p = 0; p < NP; ++p) { sn[p] = rec_s[S][p]; ta[p] = rec_tau[S][p]; }
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {        // s = tau = 0 is an exact identity: no branch
+            const int x = ALL ? rr_first(NR, S, p) : p;
+            const int y = ALL ? rr_second(NR, S, p) : BLK + (p + S) % BLK;
+#pragma unroll
+            for (int sl = 0; sl < SLOTS; ++sl) {
+              const float u = v[x][sl], w = v[y][sl];
+              v[x][sl] = fmaf(-sn[p], fmaf(ta[p], u, w), u);
+              v[y][sl] = fmaf(sn[p], fmaf(-ta[p], w, u), w);
+            }
+            if (tid < ucnt) {
+              const float u = uts[x][tid], w = uts[y][tid];
+              uts[x][tid] = fmaf(-sn[p], fmaf(ta[p], u, w), u);
+              uts[y][tid] = fmaf(sn[p], fmaf(-ta[p], w, u), w);
+            }
+          }
+        };
+        if (all) replay_all_steps<NR - 1>([&](auto st) { replay(std::integral_constant<int, 1>{}, st); });
+        else replay_all_steps<BLK>([&](auto st) { replay(std::integral_constant<int, 0>{}, st); });
+        tick(3);
+#pragma unroll
+        for (int x = 0; x < NR; ++x) {
+          const int p = srow[x];
+          if (p >= 0) {
+            float* dst = a.M + (size_t)smrow[x] * Cc;
+#pragma unroll
+            for (int sl = 0; sl < SLOTS; ++sl) {
+              const int c = c0 + tid + CL_THREADS * sl;
+              if (c < c1) __stcg(dst + c, v[x][sl]);
+            }
+            if (tid < ucnt) __stcg(a.Ut + (size_t)p * R + u0 + tid, uts[x][tid]);
+          }
+        }
+        if (tid == 0 && crank == 0) {
+          atomicAdd(&a.iscal[TRMPS_I_SVD_ROT + sweep], 1);
+          atomicMax(&a.iscal[TRMPS_I_SVD_ROT + 32 + (sweep & 31)], __float_as_int(smax));
+        }
+      }
+      // ---- publish: my slice of both blocks is up to date for round ground+1
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        if (bi < nb) *reinterpret_cast<volatile int*>(&ca.flags[bi * CL_SIZE + crank]) = ground + 1;
+        if (bj < nb) *reinterpret_cast<volatile int*>(&ca.flags[bj * CL_SIZE + crank]) = ground + 1;
+      }
+      tick(4);
+    }
+    grid.sync();
+    tick(5);
+    sweeps_used = sweep + 1;
+    const int nrot = __ldcg(&a.iscal[TRMPS_I_SVD_ROT + sweep]);
+    const float worst = __int_as_float(__ldcg(&a.iscal[TRMPS_I_SVD_ROT + 32 + (sweep & 31)]));
+    if (nrot == 0 || worst < 2e-4f) break;
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    a.iscal[TRMPS_I_SVD_SWEEPS] = sweeps_used;
+    if (a.dbg) for (int k = 0; k < 8; ++k) a.dbg[k] = (float)tacc[k];
+  }
+}
+
+__global__ void svd_zero_flags_kernel(int32_t* flags, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = 0;
+}
+
+template <int SLOTS>
+static cudaError_t launch_jacobi_cluster(SvdClArgs& ca, int nclusters, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * CL_SIZE);
+  cfg.blockDim = dim3(CL_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = CL_SIZE; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, svd_jacobi_cluster_kernel<SLOTS>, ca);
 }
 
 // sigma, ordering, m, dims update                                     optimizer.py:294-302
@@ -430,6 +736,7 @@ int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, 
   a.norms = s->work + lay.sv;
   a.rowmap = reinterpret_cast<int32_t*>(s->work + lay.sv + 2 * R);
   a.tol = 5.9604645e-8f * sqrtf((float)Cc);
+  a.dbg = s->work + lay.red;
   a.max_sweeps = opt->max_svd_sweeps > 0 ? (opt->max_svd_sweeps < 30 ? opt->max_svd_sweeps : 30) : 30;
   svd_norms_kernel<<<(R * 32 + 255) / 256, 256, 0, st>>>(a);
   TRMPS_LAUNCH_OK("svd_norms_kernel");
@@ -438,20 +745,50 @@ int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, 
   svd_init_ut_kernel<<<(R + 255) / 256, 256, 0, st>>>(a);
   TRMPS_LAUNCH_OK("svd_init_ut_kernel");
 
-  const int nb = (R + blk - 1) / blk;
-  const int ncta = ((nb + (nb & 1)) / 2) > 1 ? (nb + (nb & 1)) / 2 : 1;
-  const int slots = (Cc + SVD_THREADS - 1) / SVD_THREADS;
-  int rc;
-  if (blk == 8) {
-    if (slots <= 1) rc = launch_jacobi<16, 1>(a, ncta, st);
-    else if (slots <= 2) rc = launch_jacobi<16, 2>(a, ncta, st);
-    else if (slots <= 3) rc = launch_jacobi<16, 3>(a, ncta, st);
-    else rc = launch_jacobi<16, 5>(a, ncta, st);
-  } else {
-    if (slots <= 8) rc = launch_jacobi<8, 8>(a, ncta, st);
-    else rc = launch_jacobi<8, 10>(a, ncta, st);
+  int rc = TRMPS_OK;
+  bool done = false;
+  // preferred: cluster kernel (8 CTAs per block pair)
+  {
+    SvdClArgs ca;
+    ca.a = a;
+    ca.cols_per_cta = (Cc + CL_SIZE - 1) / CL_SIZE;
+    ca.ucols_per_cta = (R + CL_SIZE - 1) / CL_SIZE;
+    ca.flags = reinterpret_cast<int32_t*>(s->work + lay.red + 32);
+    const int slots = (ca.cols_per_cta + CL_THREADS - 1) / CL_THREADS;
+    const int nbk = (R + CL_NR / 2 - 1) / (CL_NR / 2);
+    const int ncl = ((nbk + (nbk & 1)) / 2) > 1 ? (nbk + (nbk & 1)) / 2 : 1;
+    static bool cluster_ok = true;
+    if (cluster_ok && slots <= 4 && ca.ucols_per_cta <= CL_MAXU && (nbk + 1) * CL_SIZE <= 2048) {
+      svd_zero_flags_kernel<<<((nbk + 1) * CL_SIZE + 255) / 256, 256, 0, st>>>(ca.flags, (nbk + 1) * CL_SIZE);
+      TRMPS_LAUNCH_OK("svd_zero_flags_kernel");
+      cudaError_t e = slots <= 1 ? launch_jacobi_cluster<1>(ca, ncl, st)
+                    : slots <= 2 ? launch_jacobi_cluster<2>(ca, ncl, st)
+                    : slots <= 3 ? launch_jacobi_cluster<3>(ca, ncl, st)
+                                 : launch_jacobi_cluster<4>(ca, ncl, st);
+      if (e == cudaSuccess) {
+        count_launch();
+        done = true;
+      } else {
+        (void)cudaGetLastError();      // cluster + cooperative launch refused: use the single-CTA kernel from now on
+        cluster_ok = false;
+      }
+    }
   }
-  if (rc) return rc;
+  if (!done) {
+    const int nb = (R + blk - 1) / blk;
+    const int ncta = ((nb + (nb & 1)) / 2) > 1 ? (nb + (nb & 1)) / 2 : 1;
+    const int slots = (Cc + SVD_THREADS - 1) / SVD_THREADS;
+    if (blk == 8) {
+      if (slots <= 1) rc = launch_jacobi<16, 1>(a, ncta, st);
+      else if (slots <= 2) rc = launch_jacobi<16, 2>(a, ncta, st);
+      else if (slots <= 3) rc = launch_jacobi<16, 3>(a, ncta, st);
+      else rc = launch_jacobi<16, 5>(a, ncta, st);
+    } else {
+      if (slots <= 8) rc = launch_jacobi<8, 8>(a, ncta, st);
+      else rc = launch_jacobi<8, 10>(a, ncta, st);
+    }
+    if (rc) return rc;
+  }
 
   SvdFinArgs f;
   f.M = a.M; f.R = R; f.Cc = Cc; f.Ds = Ds; f.d_near = g.d_near; f.d_far = g.d_far; f.L = L; f.rowmap = a.rowmap;

@@ -106,9 +106,12 @@ def initial_nodes(N, d, L, loc=None, weight=None, bias=None, dtype=np.float32):
     return nodes, loc
 
 
+COS_SIN_SCALE = 0.7893698     # exp(-E[log(cos(pi x/2) + sin(pi x/2))]), x ~ U[0,1)
+
+
 def random_full_bond_mps(N, d, L, D, loc=0, seed=1, noise=None, dtype=np.float32):
-    """Full-bond initial MPS for fixed-D throughput runs: near-identity
-    site tensors plus N(0, s^2) noise, s = 0.1/sqrt(D); outer dims stay 2L (mps.py:451,:462).
+    """Full-bond initial MPS for fixed-D throughput runs: COS_SIN_SCALE * identity on both
+    feature components plus N(0, s^2) noise, s = 0.1/sqrt(D); outer dims stay 2L (mps.py:451,:462).
     Not a reference function: the reference can only reach bond D by training."""
     rng = np.random.default_rng(seed)
     if noise is None:
@@ -119,11 +122,9 @@ def random_full_bond_mps(N, d, L, D, loc=0, seed=1, noise=None, dtype=np.float32
         Dl, Dr = dims[i], dims[i + 1]
         base = np.zeros((d, Dl, Dr))
         k = min(Dl, Dr)
-        base[0, :k, :k] = np.eye(k)
+        base[:, :k, :k] = np.eye(k) * COS_SIN_SCALE
         if i == loc:
-            node = np.zeros((L, d, Dl, Dr))
-            for l in range(L):
-                node[l] = base * 0.5 + rng.normal(0.0, noise, size=(d, Dl, Dr))
+            node = base[None] + rng.normal(0.0, noise, size=(L, d, Dl, Dr))
         else:
             node = base + rng.normal(0.0, noise, size=(d, Dl, Dr))
         nodes.append(node.astype(dtype))

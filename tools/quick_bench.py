@@ -59,6 +59,8 @@ def main():
     print("merge+split(+reset)           min %.3f ms  med %.3f ms  sweeps=%d m=%d" % (*t, iw[nat.I_SVD_SWEEPS], iw[nat.I_M]))
     ns = int(iw[nat.I_SVD_SWEEPS])
     print("  CTAs that rotated per sweep:", iw[8:8 + ns].tolist())
+    ph = st.work[st.layout.red:st.layout.red + 8].cpu().numpy()
+    print("  CTA0 phase cycles (load, gram, rotate, replay, store+publish, gridsync, flagwait, -):", [int(x) for x in ph], " total %.2f ms @1.9GHz" % (ph.sum() / 1.9e6))
     print("  max rel off-diagonal per sweep:", ["%.1e" % x for x in iw[40:40 + ns].view(np.float32).tolist()])
 
     def full():
