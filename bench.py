@@ -141,7 +141,7 @@ def cpu_sweep_rate(B_s, bonds, D, L, seed=0, reps=1):
     for _ in range(reps):
         t0 = time.perf_counter()
         C1s, C2s = o.setup_environments(nodes, loc, phi, L)
-        o.sweep_right(nodes, loc, loc + bonds, C1s, C2s, phi, lab, 1e-3, p)
+        o.sweep_right(nodes, loc, loc + bonds, C1s, C2s, phi, lab, 1e-5, p)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return B_s * bonds / best, best, os.cpu_count()
@@ -184,7 +184,7 @@ def run_ours(args, rank, local_rank, world):
     N, D, L, B = CFG["N"], CFG["D"], CFG["L"], args.images_per_gpu
     bonds = N - 1
     loc = 0
-    lr = 1e-3
+    lr = 1e-5          # the gradient is a SUM over the batch (optimizer.py:249): 60k images need a small rate; Armijo halves from here
     pix, lab = synthetic_pixels(N, B, L, seed=100 + rank)
     nodes = full_bond_mps(N, 2, L, D, loc)
 
