@@ -111,6 +111,7 @@ typedef struct {
   int64_t total;                         /* floats the caller must allocate for `work` */
   int32_t gsplit, nsplit;                /* split-K factor of the gradient, column split of the forward */
   int32_t red_rows, svd_block;           /* rows of `red`; rows per Jacobi block */
+  int32_t gsplit_tc, reserved0;          /* split-K factor of the tensor-core gradient kernel */
 } trmps_layout;
 
 /* one rank's view of a training batch + model; replaces the placeholders and TensorArrays that
@@ -152,6 +153,7 @@ typedef struct {
 int         trmps_abi_version(void);
 const char* trmps_last_error(void);
 int         trmps_device_check(int device);             /* TRMPS_OK if `device` is an sm_100 GPU */
+int         trmps_set_option(int32_t option, int32_t value); /* option 0: gradient kernel, 0 = tcgen05 3xTF32 (default), 1 = FP32 SIMT */
 int64_t     trmps_launch_count(void);                   /* kernels launched by this library so far (process-wide) */
 
 /* optional device-side timing of the kernels a sweep launches (CUDA events on the caller's stream; replaces the

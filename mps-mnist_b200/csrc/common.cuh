@@ -150,6 +150,9 @@ int launch_merge(const float* special, const float* far_node, float* M, int Ds, 
 int launch_grad(const float* e_near, const float* e_far, const float* phi_near, const float* sres, float* gpart, int gsplit,
                 int64_t B, int Ds, int L, bool squared, cudaStream_t st);
 int launch_sum_parts(const float* part, int nparts, int64_t n, float* out, cudaStream_t st);
+int launch_grad_tc(const float* e_near, const float* e_far, const float* phi_near, const float* sres, float* gpart, int gsplit,
+                   int64_t B, int Ds, int L, cudaStream_t st);
+int grad_tc_splits(int64_t B, int Ds, int L, int sms);
 int forward_rq(int Ds, int L);
 int svd_block_rows(int R, int Cc);
 

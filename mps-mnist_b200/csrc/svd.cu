@@ -436,17 +436,29 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
       }
       __syncthreads();
       tick(6);
-      // ---- load my column slice of the NR rows (registers) and of their U^T rows (shared)
+      // ---- load my column slice of the NR rows (registers) and of their U^T rows (shared).  All global loads are
+      //      issued before the first dependent instruction so that their latencies overlap.
+      {
+        float utmp[NR];
 #pragma unroll
-      for (int x = 0; x < NR; ++x) {
-        const int p = srow[x];
-        const float* src = a.M + (size_t)smrow[x] * Cc;
-#pragma unroll
-        for (int sl = 0; sl < SLOTS; ++sl) {
-          const int c = c0 + tid + CL_THREADS * sl;
-          v[x][sl] = (p >= 0 && c < c1) ? __ldcg(src + c) : 0.f;
+        for (int x = 0; x < NR; ++x) {
+          const int p = srow[x];
+          utmp[x] = (p >= 0 && tid < ucnt) ? __ldcg(a.Ut + (size_t)p * R + u0 + tid) : 0.f;
         }
-        if (tid < ucnt) uts[x][tid] = p >= 0 ? __ldcg(a.Ut + (size_t)p * R + u0 + tid) : 0.f;
+#pragma unroll
+        for (int x = 0; x < NR; ++x) {
+          const int p = srow[x];
+          const float* src = a.M + (size_t)smrow[x] * Cc;
+#pragma unroll
+          for (int sl = 0; sl < SLOTS; ++sl) {
+            const int c = c0 + tid + CL_THREADS * sl;
+            v[x][sl] = (p >= 0 && c < c1) ? __ldcg(src + c) : 0.f;
+          }
+        }
+        if (tid < ucnt) {
+#pragma unroll
+          for (int x = 0; x < NR; ++x) uts[x][tid] = utmp[x];
+        }
       }
       tick(0);
       // ---- Gram partials of my slice (upper triangle, row-major), reduced over the CTA

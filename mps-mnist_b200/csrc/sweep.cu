@@ -50,6 +50,8 @@ ProfScope::~ProfScope() {
   ++g_prof_n;
 }
 
+static int g_grad_impl = 0;   // 0 = tcgen05 3xTF32, 1 = FP32 SIMT
+
 static int g_sm_count = 0;
 static int sm_count() {
   if (g_sm_count == 0) {
@@ -104,7 +106,8 @@ static int compute_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, int32_t s
   o->gradM = off; off += a4(RC + TRMPS_S_COUNT);
   o->deltaM = off; off += a4(RC);
   o->hessM = off; off += a4(RC + TRMPS_S_COUNT);
-  o->gpart = off; off += a4(gs * RC);
+  const int gs_tc = grad_tc_splits(B, Ds, L, sms);
+  o->gpart = off; off += a4((gs > gs_tc ? gs : gs_tc) * RC);
   o->f0 = off; off += a4(B * L);
   o->fd = off; off += a4(B * L);
   o->fpart = off; off += a4((int64_t)best * B * L);
@@ -123,6 +126,8 @@ static int compute_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, int32_t s
   o->nsplit = best;
   o->red_rows = (int32_t)rr;
   o->svd_block = svd_block_rows((int)R, (int)Cc);
+  o->gsplit_tc = gs_tc;
+  o->reserved0 = 0;
   return TRMPS_OK;
 }
 
@@ -217,8 +222,13 @@ static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const Bond
   }
   {
     ProfScope ps(PROF_GRAD, st);
-    if ((rc = launch_grad(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit, s->B, Ds, L, false, st))) return rc;
-    if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit, RC, w + lay.gradM, st))) return rc;
+    if (g_grad_impl == 0) {
+      if ((rc = launch_grad_tc(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit_tc, s->B, Ds, L, st))) return rc;
+      if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit_tc, RC, w + lay.gradM, st))) return rc;
+    } else {
+      if ((rc = launch_grad(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit, s->B, Ds, L, false, st))) return rc;
+      if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit, RC, w + lay.gradM, st))) return rc;
+    }
   }
   {
     ProfScope ps(PROF_COMM, st);
@@ -360,6 +370,12 @@ using namespace trmps;
 // ================================================================================================= C ABI
 extern "C" int trmps_abi_version(void) { return TRMPS_ABI_VERSION; }
 extern "C" int64_t trmps_launch_count(void) { return (int64_t)g_launches; }
+
+extern "C" int trmps_set_option(int32_t option, int32_t value) {
+  if (option == 0 && (value == 0 || value == 1)) { g_grad_impl = value; return TRMPS_OK; }
+  set_error("trmps_set_option: unknown option %d / value %d", option, value);
+  return TRMPS_E_ARG;
+}
 
 extern "C" int trmps_profile_begin(int32_t max_records) {
   if (max_records <= 0) { set_error("trmps_profile_begin: max_records must be positive"); return TRMPS_E_ARG; }

@@ -32,7 +32,7 @@ class Layout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
                 ("bondM", "gradM", "deltaM", "hessM", "gpart", "f0", "fd", "fpart", "resid", "sres", "hres",
                  "phi2", "Ut", "sv", "red", "scal", "total")] + \
-               [(n, C.c_int32) for n in ("gsplit", "nsplit", "red_rows", "svd_block")]
+               [(n, C.c_int32) for n in ("gsplit", "nsplit", "red_rows", "svd_block", "gsplit_tc", "reserved0")]
 
 
 class Sweep(C.Structure):
@@ -56,6 +56,7 @@ _SIGNATURES = {
     "trmps_abi_version": (C.c_int, []),
     "trmps_last_error": (C.c_char_p, []),
     "trmps_device_check": (C.c_int, [C.c_int]),
+    "trmps_set_option": (C.c_int, [C.c_int32, C.c_int32]),
     "trmps_launch_count": (C.c_int64, []),
     "trmps_profile_begin": (C.c_int, [C.c_int32]),
     "trmps_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]),
@@ -131,6 +132,13 @@ def profile_end():
     cnt = (C.c_int32 * n)()
     check(load().trmps_profile_end(ms, cnt, n), "trmps_profile_end")
     return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(PROF_CATEGORIES)}
+
+
+OPT_GRAD_IMPL, GRAD_TCGEN05, GRAD_SIMT = 0, 0, 1
+
+
+def set_option(option, value):
+    check(load().trmps_set_option(option, value), "trmps_set_option")
 
 
 def launch_count():

@@ -324,3 +324,39 @@ def test_cuda_path_reproduces_golden(path):
     got = dev.predict(st.weights_view(), st.feat, nat.FM_ONE_SQRT3).cpu().numpy()
     assert rel(got, g['f_final_f64']) < 10 * max(rel(g['f_final'], g['f_final_f64']), 1e-4)
     assert np.mean(got.argmax(1) == g['f_final'].argmax(1)) >= 0.98
+
+
+# --------------------------------------------------------------------------------------------- tensor-core gradient
+@pytest.mark.parametrize("D,B", [(24, 700), (56, 3000), (120, 4099)])
+def test_tcgen05_gradient_matches_simt_and_fp64(D, B):
+    N, L, loc = 6, 10, 2
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=61, fm=o.FM_COS_SIN, full_bond=D, loc=loc)
+    st = make_state(N, B, L, D, nodes, loc, phi, lab)
+    st.init_env(loc)
+    st.bond_merge(loc, +1)
+    opt = dev.make_opt(lr=0.1, max_size=st.Ds, reg=0.0)
+    try:
+        nat.set_option(nat.OPT_GRAD_IMPL, nat.GRAD_SIMT)
+        st.bond_gradient(loc, +1, opt)
+        torch.cuda.synchronize()
+        g_simt = st.grad_matrix().clone().cpu().numpy()
+        nat.set_option(nat.OPT_GRAD_IMPL, nat.GRAD_TCGEN05)
+        st.grad_matrix().zero_()
+        st.bond_gradient(loc, +1, opt)
+        torch.cuda.synchronize()
+        g_tc = st.grad_matrix().clone().cpu().numpy()
+    finally:
+        nat.set_option(nat.OPT_GRAD_IMPL, nat.GRAD_TCGEN05)
+    bond, (Cn, Cf, pn, pf) = oracle_bond_setup(nodes, loc, phi, L, +1)
+    C = o.calculate_C(Cn, Cf, pn, pf).astype(np.float64)
+    h = o.softmax(st.logits0().cpu().numpy().astype(np.float64))
+    G64 = np.tensordot(lab.astype(np.float64) - h, C, axes=([0], [0]))
+    dn, df = bond.shape[3], bond.shape[4]
+    got_tc = state_bond(st, torch.from_numpy(g_tc).cuda())[:, :, :, :dn, :df]
+    got_simt = state_bond(st, torch.from_numpy(g_simt).cuda())[:, :, :, :dn, :df]
+    assert rel(got_simt, G64) < 1e-5
+    assert rel(got_tc, G64) < 1e-5                      # 3xTF32 keeps FP32-level accuracy (tolerance is 1e-4)
+    assert rel(g_tc, g_simt) < 1e-5
+    pad = g_tc.copy().reshape(2, st.Ds, L, 2, st.Ds)
+    pad[:, :dn, :, :, :df] = 0
+    assert np.all(pad == 0)

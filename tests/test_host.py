@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_the_header_layout():
     import ctypes as C
     assert C.sizeof(nat.Opt) == 40
-    assert C.sizeof(nat.Layout) == 17 * 8 + 4 * 4
+    assert C.sizeof(nat.Layout) == 17 * 8 + 6 * 4
     assert C.sizeof(nat.Sweep) == 4 * 4 + 2 * 8 + 2 * 4 + 10 * 8
     assert C.sizeof(nat.PredictDesc) == 4 * 4 + 8 + 4 * 4 + 6 * 8
 
