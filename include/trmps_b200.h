@@ -108,6 +108,7 @@ typedef struct {
   int64_t sv;                            /* 3R: singular values (descending), int32 order, int32 row map */
   int64_t red;                           /* per-CTA partial sums of the scalar reductions */
   int64_t scal;                          /* TRMPS_S_COUNT floats */
+  int64_t bimg;                          /* TF32 hi/lo shared-memory images of the bond for the tensor-core forward */
   int64_t total;                         /* floats the caller must allocate for `work` */
   int32_t gsplit, nsplit;                /* split-K factor of the gradient, column split of the forward */
   int32_t red_rows, svd_block;           /* rows of `red`; rows per Jacobi block */
@@ -153,7 +154,7 @@ typedef struct {
 int         trmps_abi_version(void);
 const char* trmps_last_error(void);
 int         trmps_device_check(int device);             /* TRMPS_OK if `device` is an sm_100 GPU */
-int         trmps_set_option(int32_t option, int32_t value); /* option 0: gradient kernel, 0 = tcgen05 3xTF32 (default), 1 = FP32 SIMT */
+int         trmps_set_option(int32_t option, int32_t value); /* option 0: gradient kernel, option 1: forward kernel; value 0 = tcgen05 3xTF32 (default), 1 = FP32 SIMT */
 int64_t     trmps_launch_count(void);                   /* kernels launched by this library so far (process-wide) */
 
 /* optional device-side timing of the kernels a sweep launches (CUDA events on the caller's stream; replaces the

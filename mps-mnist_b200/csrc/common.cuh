@@ -153,6 +153,11 @@ int launch_sum_parts(const float* part, int nparts, int64_t n, float* out, cudaS
 int launch_grad_tc(const float* e_near, const float* e_far, const float* phi_near, const float* sres, float* gpart, int gsplit,
                    int64_t B, int Ds, int L, cudaStream_t st);
 int grad_tc_splits(int64_t B, int Ds, int L, int sms);
+bool forward_tc_supported(int Ds, int L, int nd);
+int64_t forward_tc_image_floats(int Ds, int L);
+int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_near, const float* phi_far, const float* M,
+                      float* bimg, float* f_out, int64_t B, int Ds, int L, const int32_t* d_near, const int32_t* d_far,
+                      cudaStream_t st);
 int forward_rq(int Ds, int L);
 int svd_block_rows(int R, int Cc);
 

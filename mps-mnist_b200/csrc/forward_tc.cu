@@ -1,0 +1,322 @@
+// Forward contraction f[t,l] of a bond matrix on the 5th-generation tensor cores (north_star piece 3;
+// optimizer.py:222-227: f = tensordot(C, bond), without ever forming C).
+//
+//   X[t, (k; l,m,n)] = sum_i e_near[t,i] * Bm[(m,i), (l,n,k)]          GEMM  M = images, K = near bond, N = 4*L*Ds
+//   f[t,l]           = sum_{k,m,n} X[t,(k;l,m,n)] * phi_near[t,m] phi_far[t,n] e_far[t,k]      epilogue
+//
+// The feature vectors are moved out of the GEMM into the epilogue weight, so the A operand is the raw
+// environment tile (split once into TF32 hi/lo, K-major SWIZZLE_128B, resident in shared memory for the whole
+// CTA) and the B operand is the bond itself.  The bond is re-laid-out once per call (prep kernel, 2.3 MB) into
+// ready-made hi/lo shared-memory images whose columns are ordered (k; l,m,n): a 16*L-column tile then holds 4
+// values of k times all 4*L (l,m,n) combinations, which makes the epilogue completely static -- every
+// accumulator column has a compile-time (k_local, l, m, n), the weights are 4 + 4 registers per tile and the
+// per-label sums live in registers.  3xTF32 (hi*hi + lo*hi + hi*lo) keeps FP32-level accuracy.
+//
+// Warp roles (192 threads): warps 0-3 epilogue (one TMEM lane quadrant each), warp 4 issues the MMAs, warp 5
+// streams the B images with cp.async.bulk into a 3-stage mbarrier ring.  The accumulator is double buffered in
+// TMEM so the epilogue of tile j overlaps the MMAs of tile j+1.
+#include "common.cuh"
+
+namespace trmps {
+
+namespace {
+
+constexpr int FT_THREADS = 192;
+constexpr int FT_TM = 128;                 // images per CTA
+constexpr int FT_KMAX = 128;               // near bond (padded) handled by the resident A tile
+constexpr int FT_KCH = 16;                 // near-bond indices per B stage
+constexpr int FT_STAGES = 3;
+constexpr int FT_A_BYTES = FT_TM * FT_KMAX * 4;      // 64 KB per (hi | lo)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) { } }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+// smem matrix descriptor: layout 2 = SWIZZLE_128B (K-major A), 1 = SWIZZLE_128B_BASE32B (MN-major B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+// byte offset inside one B image (MN extent NT columns, 16 k): SWIZZLE_128B_BASE32B, groups of 4 k are NT/32 atoms apart
+__host__ __device__ __forceinline__ uint32_t bimg_off(int col, int k, int nt) {
+  const int blk = col >> 5, c32 = (col & 31) >> 3, e = col & 7, kg = k >> 2, k4 = k & 3;
+  return (uint32_t)((kg * (nt / 32) + blk) * 512 + k4 * 128 + ((c32 ^ k4) << 5) + e * 4);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// prep: bond matrix M (R x Cc; rows (m,i), cols (l,n,k)) -> hi/lo B images, [tile j][chunk q][hi|lo][image bytes]
+// tile j holds k = 4j .. 4j+3, column inside the tile = k_local*(4L) + l*4 + m*2 + n ; chunk q holds i = 16q .. 16q+15
+template <int L>
+__global__ void forward_prep_kernel(const float* __restrict__ M, float* __restrict__ bimg, int Ds, int ntiles, int nchunks) {
+  constexpr int NT = 16 * L, IMG = 16 * NT;   // floats per (hi | lo) image
+  const int64_t Cc = (int64_t)2 * L * Ds;
+  const int64_t total = (int64_t)ntiles * nchunks * IMG;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(e % NT);
+    const int il = (int)((e / NT) % 16);
+    const int64_t jq = e / IMG;
+    const int q = (int)(jq % nchunks), j = (int)(jq / nchunks);
+    const int kl = col / (4 * L), r = col % (4 * L), l = r >> 2, m = (r >> 1) & 1, n = r & 1;
+    const int k = 4 * j + kl, i = 16 * q + il;
+    float v = 0.f;
+    if (k < Ds && i < Ds) v = M[(int64_t)(m * Ds + i) * Cc + (int64_t)(l * 2 + n) * Ds + k];
+    const float hi = tf32_round(v), lo = tf32_round(v - hi);
+    float* img = bimg + jq * (2 * IMG);
+    const uint32_t off = bimg_off(col, il, NT) >> 2;
+    img[off] = hi;
+    img[IMG + off] = lo;
+  }
+}
+
+struct FwdTcArgs {
+  const float* e_near; const float* e_far; const float* phi_near; const float* phi_far; const float* bimg;
+  float* f; int64_t B; int Ds; const int32_t* d_near; const int32_t* d_far; int nchunks_max;
+};
+
+template <int L>
+__global__ void __launch_bounds__(FT_THREADS, 1) forward_tc_kernel(FwdTcArgs a) {
+  constexpr int NT = 16 * L;                         // accumulator columns per tile
+  constexpr int IMG_BYTES = 16 * NT * 4;             // one (hi | lo) B image
+  constexpr int STAGE_BYTES = 2 * IMG_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * NT <= 64 ? 64 : 2 * NT <= 128 ? 128 : 2 * NT <= 256 ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_hi = smem;
+  uint8_t* a_lo = smem + FT_A_BYTES;
+  uint8_t* bst = smem + 2 * FT_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bst + FT_STAGES * STAGE_BYTES);
+  uint64_t* b_full = bars, *b_empty = bars + FT_STAGES, *acc_full = bars + 2 * FT_STAGES, *acc_empty = bars + 2 * FT_STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FT_STAGES + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Ds = a.Ds;
+  const int64_t t0 = (int64_t)blockIdx.x * FT_TM;
+  const int dn = __ldg(a.d_near), df = __ldg(a.d_far);
+  const int nchunks = (dn + FT_KCH - 1) / FT_KCH;       // K chunks actually needed
+  const int ntiles = (df + 3) / 4;                      // column tiles actually needed (4 k per tile)
+
+  if (tid == 0) {
+    for (int s = 0; s < FT_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+
+  // ---- A tile: e_near rows of my 128 images, split into tf32 hi / lo, K-major SWIZZLE_128B
+  //      element (row t, k): atom (kb = k/32, tb = t/8) at (kb*16 + tb)*1024, row t%8 of 128 B, 16-byte chunk (k%32)/4 ^ (t%8)
+  {
+    const int kq = nchunks * FT_KCH / 4;      // float4 columns to fill (multiple of 4)
+    for (int e = tid; e < FT_TM * kq; e += FT_THREADS) {
+      const int t = e / kq, k4 = e - t * kq, k = 4 * k4;
+      const int64_t tg = t0 + t;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tg < a.B && k < Ds) v = __ldg(reinterpret_cast<const float4*>(a.e_near + tg * Ds + k));
+      float4 hi, lo;
+      hi.x = tf32_round(v.x); hi.y = tf32_round(v.y); hi.z = tf32_round(v.z); hi.w = tf32_round(v.w);
+      lo.x = tf32_round(v.x - hi.x); lo.y = tf32_round(v.y - hi.y); lo.z = tf32_round(v.z - hi.z); lo.w = tf32_round(v.w - hi.w);
+      const int kb = k >> 5, tb = t >> 3, r = t & 7, ch = (k & 31) >> 2;
+      const uint32_t off = (uint32_t)((kb * 16 + tb) * 1024 + r * 128 + ((ch ^ r) << 4));
+      *reinterpret_cast<float4*>(a_hi + off) = hi;
+      *reinterpret_cast<float4*>(a_lo + off) = lo;
+    }
+  }
+  fence_async_proxy();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    // ===== B loader: one elected lane streams (tile, chunk) images =====
+    if (lane == 0) {
+      int it = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        for (int q = 0; q < nchunks; ++q, ++it) {
+          const int s = it % FT_STAGES, ph = (it / FT_STAGES) & 1;
+          if (it >= FT_STAGES) mbar_wait(&b_empty[s], (uint32_t)(ph ^ 1));
+          mbar_expect_tx(&b_full[s], STAGE_BYTES);
+          const float* src = a.bimg + ((int64_t)j * a.nchunks_max + q) * (STAGE_BYTES / 4);
+          bulk_g2s(bst + s * STAGE_BYTES, src, STAGE_BYTES, &b_full[s]);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(FT_TM >> 4) << 24);
+      int it = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        const int b = j & 1;
+        if (j >= 2) mbar_wait(&acc_empty[b], (uint32_t)(((j >> 1) - 1) & 1));
+        tc_fence_after();
+        const uint32_t d = tmem_base + b * NT;
+        for (int q = 0; q < nchunks; ++q, ++it) {
+          const int s = it % FT_STAGES, ph = (it / FT_STAGES) & 1;
+          mbar_wait(&b_full[s], (uint32_t)ph);
+          tc_fence_after();
+          const uint32_t bh = smem_u32(bst + s * STAGE_BYTES), bl = bh + IMG_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < FT_KCH / 8; ++ks) {
+            const int k0 = q * FT_KCH + ks * 8;                    // first near-bond index of this K=8 step
+            const uint32_t aoff = (uint32_t)((k0 >> 5) * 16 * 1024 + ((k0 & 31) >> 3) * 32);
+            const uint64_t dah = make_desc(smem_u32(a_hi) + aoff, 16, 1024, 2);
+            const uint64_t dal = make_desc(smem_u32(a_lo) + aoff, 16, 1024, 2);
+            const uint32_t boff = (uint32_t)(2 * ks * (NT / 32) * 512);   // two groups of 4 k per MMA
+            const uint64_t dbh = make_desc(bh + boff, 512, (NT / 32) * 512, 1);
+            const uint64_t dbl = make_desc(bl + boff, 512, (NT / 32) * 512, 1);
+            const uint32_t acc = (q > 0 || ks > 0) ? 1u : 0u;
+            umma_tf32(d, dah, dbh, idesc, acc);
+            umma_tf32(d, dal, dbh, idesc, 1u);
+            umma_tf32(d, dah, dbl, idesc, 1u);
+          }
+          umma_commit(&b_empty[s]);
+        }
+        umma_commit(&acc_full[b]);
+      }
+    }
+  } else {
+    // ===== epilogue warps 0-3: TMEM lanes 32*warp .. +31, one image row per thread =====
+    const int row = warp * 32 + lane;
+    const int64_t tg = t0 + row;
+    const bool live = tg < a.B;
+    float pp[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      const float2 p1 = __ldg(reinterpret_cast<const float2*>(a.phi_near) + tg);
+      const float2 p2 = __ldg(reinterpret_cast<const float2*>(a.phi_far) + tg);
+      pp[0] = p1.x * p2.x; pp[1] = p1.x * p2.y; pp[2] = p1.y * p2.x; pp[3] = p1.y * p2.y;   // index m*2+n
+    }
+    float facc[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) facc[l] = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      const int b = j & 1;
+      float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live && 4 * j < Ds) e4 = __ldg(reinterpret_cast<const float4*>(a.e_far + tg * Ds + 4 * j));
+      const float ek[4] = {e4.x, e4.y, e4.z, e4.w};
+      mbar_wait(&acc_full[b], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int cb = 0; cb < NT / 32; ++cb) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * NT + cb * 32), v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int col = cb * 32 + e;                       // compile-time: (k_local; l, m, n)
+          const int kl = col / (4 * L), r = col % (4 * L), l = r >> 2, mn = r & 3;
+          facc[l] = fmaf(v[e], pp[mn] * ek[kl], facc[l]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+    }
+    if (live) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) a.f[tg * L + l] = facc[l];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int L>
+size_t forward_tc_smem() { return (size_t)2 * FT_A_BYTES + (size_t)FT_STAGES * 2 * 16 * 16 * L * 4 + 256 + 1024; }
+
+}  // namespace
+
+bool forward_tc_supported(int Ds, int L, int nd) { return nd == 2 && L == 10 && Ds <= FT_KMAX && Ds % 8 == 0; }
+
+// floats needed for the hi/lo B images of one bond
+int64_t forward_tc_image_floats(int Ds, int L) {
+  const int64_t ntiles = (Ds + 3) / 4, nchunks = (Ds + FT_KCH - 1) / FT_KCH;
+  return ntiles * nchunks * 2 * 16 * 16 * L;
+}
+
+int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_near, const float* phi_far, const float* M,
+                      float* bimg, float* f_out, int64_t B, int Ds, int L, const int32_t* d_near, const int32_t* d_far,
+                      cudaStream_t st) {
+  if (B <= 0) return TRMPS_OK;
+  if (!forward_tc_supported(Ds, L, 2)) {
+    set_error("forward_tc: unsupported shape Ds=%d L=%d", Ds, L);
+    return TRMPS_E_ARG;
+  }
+  const int ntiles = (Ds + 3) / 4, nchunks = (Ds + FT_KCH - 1) / FT_KCH;
+  forward_prep_kernel<10><<<592, 256, 0, st>>>(M, bimg, Ds, ntiles, nchunks);
+  TRMPS_LAUNCH_OK("forward_prep_kernel");
+  FwdTcArgs a;
+  a.e_near = e_near; a.e_far = e_far; a.phi_near = phi_near; a.phi_far = phi_far; a.bimg = bimg; a.f = f_out;
+  a.B = B; a.Ds = Ds; a.d_near = d_near; a.d_far = d_far; a.nchunks_max = nchunks;
+  const size_t smem = forward_tc_smem<10>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    TRMPS_CUDA_OK(cudaFuncSetAttribute(forward_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  forward_tc_kernel<10><<<(unsigned)ceil_div64(B, FT_TM), FT_THREADS, smem, st>>>(a);
+  TRMPS_LAUNCH_OK("forward_tc_kernel");
+  return TRMPS_OK;
+}
+
+}  // namespace trmps

@@ -51,6 +51,7 @@ ProfScope::~ProfScope() {
 }
 
 static int g_grad_impl = 0;   // 0 = tcgen05 3xTF32, 1 = FP32 SIMT
+static int g_fwd_impl = 0;    // same for the forward contraction
 
 static int g_sm_count = 0;
 static int sm_count() {
@@ -101,6 +102,8 @@ static int compute_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, int32_t s
     if (eff > best_eff + 1e-9) { best_eff = eff; best = ns; }
     if (eff >= 0.9) { best = ns; break; }
   }
+  const bool fwd_tc = g_fwd_impl == 0 && forward_tc_supported(Ds, L, 2);
+  if (fwd_tc) best = 1;      // the tensor-core forward writes complete logits
   int64_t off = 0;
   o->bondM = off; off += a4(RC);
   o->gradM = off; off += a4(RC + TRMPS_S_COUNT);
@@ -121,6 +124,7 @@ static int compute_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, int32_t s
   if (rr < 296) rr = 296;
   o->red = off; off += a4(rr * 32);
   o->scal = off; off += a4(2 * TRMPS_S_COUNT);
+  o->bimg = off; off += a4(forward_tc_supported(Ds, L, 2) ? forward_tc_image_floats(Ds, L) : 0);
   o->total = off;
   o->gsplit = (int32_t)gs;
   o->nsplit = best;
@@ -192,6 +196,9 @@ static int do_merge(const trmps_sweep* s, const trmps_layout& lay, const BondGeo
 static int do_forward(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const float* M, cudaStream_t st) {
   ProfScope ps(PROF_FORWARD, st);
   const float* phi2 = s->work + lay.phi2;
+  if (g_fwd_impl == 0 && forward_tc_supported(s->Ds, s->L, 2))
+    return launch_forward_tc(g.e_near, g.e_far, phi2, phi2 + 2 * s->B, M, s->work + lay.bimg, s->work + lay.fpart, s->B, s->Ds,
+                             s->L, g.d_near, g.d_far, st);
   return launch_forward(g.e_near, g.e_far, phi2, phi2 + 2 * s->B, M, s->work + lay.fpart, lay.nsplit, s->B, s->Ds, s->L, 2,
                         g.d_near, st);
 }
@@ -373,6 +380,7 @@ extern "C" int64_t trmps_launch_count(void) { return (int64_t)g_launches; }
 
 extern "C" int trmps_set_option(int32_t option, int32_t value) {
   if (option == 0 && (value == 0 || value == 1)) { g_grad_impl = value; return TRMPS_OK; }
+  if (option == 1 && (value == 0 || value == 1)) { g_fwd_impl = value; return TRMPS_OK; }
   set_error("trmps_set_option: unknown option %d / value %d", option, value);
   return TRMPS_E_ARG;
 }

@@ -31,7 +31,7 @@ class Opt(C.Structure):
 class Layout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
                 ("bondM", "gradM", "deltaM", "hessM", "gpart", "f0", "fd", "fpart", "resid", "sres", "hres",
-                 "phi2", "Ut", "sv", "red", "scal", "total")] + \
+                 "phi2", "Ut", "sv", "red", "scal", "bimg", "total")] + \
                [(n, C.c_int32) for n in ("gsplit", "nsplit", "red_rows", "svd_block", "gsplit_tc", "reserved0")]
 
 
@@ -135,6 +135,7 @@ def profile_end():
 
 
 OPT_GRAD_IMPL, GRAD_TCGEN05, GRAD_SIMT = 0, 0, 1
+OPT_FWD_IMPL, FWD_TCGEN05, FWD_SIMT = 1, 0, 1
 
 
 def set_option(option, value):

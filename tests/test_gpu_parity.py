@@ -360,3 +360,31 @@ def test_tcgen05_gradient_matches_simt_and_fp64(D, B):
     pad = g_tc.copy().reshape(2, st.Ds, L, 2, st.Ds)
     pad[:, :dn, :, :, :df] = 0
     assert np.all(pad == 0)
+
+
+@pytest.mark.parametrize("D,B,direction", [(24, 700, +1), (56, 3000, -1), (120, 4099, +1), (120, 300, -1)])
+def test_tcgen05_forward_matches_simt_and_fp64(D, B, direction):
+    N, L, loc = 6, 10, 2
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=71, fm=o.FM_COS_SIN, full_bond=D, loc=loc)
+    results = {}
+    try:
+        for impl in (nat.FWD_SIMT, nat.FWD_TCGEN05):
+            nat.set_option(nat.OPT_FWD_IMPL, impl)
+            st = make_state(N, B, L, D, nodes, loc, phi, lab)       # layout (nsplit) depends on the option
+            st.init_env(loc)
+            if direction < 0:
+                lib = nat.load()
+                nat.check(lib.trmps_env_step(st.feat[loc + 1].data_ptr(), nat.FM_PRECOMPUTED, B, st.Ds, -1,
+                                             st.envR[loc + 1].data_ptr(), st.slots[loc + 1].data_ptr(),
+                                             st.dims[loc + 2:].data_ptr(), st.envR[loc].data_ptr(), None), "env_step")
+            st.bond_merge(loc, direction)
+            st.bond_forward(loc, direction, 0)
+            torch.cuda.synchronize()
+            results[impl] = st.logits0().clone().cpu().numpy()
+    finally:
+        nat.set_option(nat.OPT_FWD_IMPL, nat.FWD_TCGEN05)
+    bond, (Cn, Cf, pn, pf) = oracle_bond_setup(nodes, loc, phi, L, direction)
+    f64 = o.forward_factored(bond.astype(np.float64), Cn.astype(np.float64), Cf.astype(np.float64), pn.astype(np.float64), pf.astype(np.float64))
+    assert rel(results[nat.FWD_SIMT], f64) < 1e-5
+    assert rel(results[nat.FWD_TCGEN05], f64) < 1e-5
+    assert np.array_equal(results[nat.FWD_TCGEN05].argmax(1), f64.argmax(1)) or rel(results[nat.FWD_TCGEN05], f64) < 1e-6
