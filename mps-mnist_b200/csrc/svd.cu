@@ -354,20 +354,30 @@ __device__ __forceinline__ void pair_of_row(int all, int step, int row, int& x, 
   else { pidx = (NR - 1) - j; y = row; x = (step + pidx) % (NR - 1); }
 }
 
-// rotation that annihilates the (x,y) entry of a 2x2 Gram [[al, ga],[ga, be]]: x' = c x - s y, y' = s x + c y
+// rotation that annihilates the (x,y) entry of a 2x2 Gram [[al, ga],[ga, be]]: x' = c x - s y, y' = s x + c y.
+// Half-angle form: cos 2t = |be-al| / hyp, sin 2t = sgn * 2|ga| / hyp, c = sqrt((1 + cos 2t)/2), s = sin 2t / (2c);
+// three dependent special-function ops (rsqrt, rsqrt, rcp) instead of six, no divergent branches.
 __device__ __forceinline__ bool rotation_params(float al, float be, float ga, float tol, float& c, float& s, float& tau, float& relg) {
-  c = 1.f; s = 0.f; tau = 0.f; relg = 0.f;
   const float big = fmaxf(al, be), small = fminf(al, be);
-  if (!(small > 1e-30f && small > 1e-24f * big)) return false;
   relg = fabsf(ga) * rsqrtf(al) * rsqrtf(be);
-  if (!(relg > tol)) return false;
-  const float zeta = __fdividef(be - al, 2.f * ga);
-  const float h2 = fmaf(zeta, zeta, 1.f);
-  const float t = __fdividef(copysignf(1.f, zeta), fabsf(zeta) + h2 * rsqrtf(h2));
-  c = rsqrtf(fmaf(t, t, 1.f));
-  s = c * t;
-  tau = __fdividef(s, 1.f + c);
-  return true;
+  const bool rot = small > 1e-30f && small > 1e-24f * big && relg > tol;
+  // scale by a power of two near 1/max(al,be) (exponent arithmetic, no special-function op) so that the squares
+  // below neither underflow for tiny rows nor overflow for huge ones
+  const int ebig = (__float_as_int(big) >> 23) & 0xff;
+  const float scale = __int_as_float(max(1, min(253, 254 - ebig)) << 23);
+  const float d = (be - al) * scale, gs = ga * scale;
+  const float rh = rsqrtf(fmaxf(fmaf(d, d, 4.f * gs * gs), 1e-37f));   // 1 / hyp
+  const float c2 = fabsf(d) * rh;                               // cos 2t  (>= 0)
+  const float x = fmaf(0.5f, c2, 0.5f);                         // cos^2 t in [0.5, 1]
+  const float rc = rsqrtf(x);                                   // 1 / c
+  const float cc = x * rc;
+  const float sg = (d >= 0.f) ? 1.f : -1.f;
+  const float ss = sg * gs * rh * rc;                           // sin 2t / (2 c), sin 2t = sg * 2 ga / hyp
+  c = rot ? cc : 1.f;
+  s = rot ? ss : 0.f;
+  tau = rot ? __fdividef(ss, 1.f + cc) : 0.f;
+  relg = rot ? relg : 0.f;
+  return rot;
 }
 
 template <int SLOTS>
@@ -511,28 +521,38 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
       {
         const int i = tid / NR, j = tid % NR, pl = lane & 7;
         float worst_rel = 0.f;
+        // pairing data of the step (constant tables): fetched one step ahead, off the critical path
+        int px = tab_x[all][0][pl], py = tab_y[all][0][pl];
+        int qi = tab_pidx[all][0][i], qj = tab_pidx[all][0][j];
+        int opi = tab_partner[all][0][i], opj = tab_partner[all][0][j];
+        int fi = tab_first[all][0][i], fj = tab_first[all][0][j];
         for (int step = 0; step < nsteps; ++step) {
-          const int px = tab_x[all][step][pl], py = tab_y[all][step][pl];
+          const float al = Gs[cur][px][px], be = Gs[cur][py][py], ga = Gs[cur][px][py];
+          const bool okp = srow[px] >= 0 && srow[py] >= 0;
+          const float gij = Gs[cur][i][j], gipj = Gs[cur][i][opj], gpij = Gs[cur][opi][j], gpipj = Gs[cur][opi][opj];
+          const int cqi = qi, cqj = qj, cfi = fi, cfj = fj;
+          if (step + 1 < nsteps) {
+            px = tab_x[all][step + 1][pl]; py = tab_y[all][step + 1][pl];
+            qi = tab_pidx[all][step + 1][i]; qj = tab_pidx[all][step + 1][j];
+            opi = tab_partner[all][step + 1][i]; opj = tab_partner[all][step + 1][j];
+            fi = tab_first[all][step + 1][i]; fj = tab_first[all][step + 1][j];
+          }
           float c, sn, tau, relg;
-          bool rot = rotation_params(Gs[cur][px][px], Gs[cur][py][py], Gs[cur][px][py], a.tol, c, sn, tau, relg);
-          if (!(srow[px] >= 0 && srow[py] >= 0)) { rot = false; c = 1.f; sn = 0.f; tau = 0.f; }
-          const int qi = tab_pidx[all][step][i], qj = tab_pidx[all][step][j];
-          const float ci = __shfl_sync(0xffffffffu, c, qi), si = __shfl_sync(0xffffffffu, sn, qi);
-          const float cj = __shfl_sync(0xffffffffu, c, qj), sj = __shfl_sync(0xffffffffu, sn, qj);
-          const int opi = tab_partner[all][step][i], opj = tab_partner[all][step][j];
-          const float bi_ = tab_first[all][step][i] ? -si : si, bj_ = tab_first[all][step][j] ? -sj : sj;
-          float g = ci * cj * Gs[cur][i][j];
-          g = fmaf(ci * bj_, Gs[cur][i][opj], g);
-          g = fmaf(bi_ * cj, Gs[cur][opi][j], g);
-          g = fmaf(bi_ * bj_, Gs[cur][opi][opj], g);
+          bool rot = rotation_params(al, be, ga, a.tol, c, sn, tau, relg);
+          if (!okp) { rot = false; c = 1.f; sn = 0.f; tau = 0.f; relg = 0.f; }
+          const float ci = __shfl_sync(0xffffffffu, c, cqi), si = __shfl_sync(0xffffffffu, sn, cqi);
+          const float cj = __shfl_sync(0xffffffffu, c, cqj), sj = __shfl_sync(0xffffffffu, sn, cqj);
+          const float bi_ = cfi ? -si : si, bj_ = cfj ? -sj : sj;
+          float g = ci * cj * gij;
+          g = fmaf(ci * bj_, gipj, g);
+          g = fmaf(bi_ * cj, gpij, g);
+          g = fmaf(bi_ * bj_, gpipj, g);
           Gs[cur ^ 1][i][j] = g;
           if (tid < NP) {                 // warp 0, lanes 0..7: one lane per pair records the rotation
             rec_s[step][tid] = sn;
             rec_tau[step][tid] = tau;
-            if (rot) {
-              sflag = 1;
-              worst_rel = fmaxf(worst_rel, relg);
-            }
+            if (rot) sflag = 1;
+            worst_rel = fmaxf(worst_rel, relg);
           }
           __syncthreads();
           cur ^= 1;
@@ -586,10 +606,11 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
           atomicMax(&a.iscal[TRMPS_I_SVD_ROT + 32 + (sweep & 31)], __float_as_int(smax));
         }
       }
-      // ---- publish: my slice of both blocks is up to date for round ground+1
-      __threadfence();
+      // ---- publish: my slice of both blocks is up to date for round ground+1 (the barrier orders every thread's
+      //      stores before thread 0's fence, which is cumulative)
       __syncthreads();
       if (tid == 0) {
+        __threadfence();
         if (bi < nb) *reinterpret_cast<volatile int*>(&ca.flags[bi * CL_SIZE + crank]) = ground + 1;
         if (bj < nb) *reinterpret_cast<volatile int*>(&ca.flags[bj * CL_SIZE + crank]) = ground + 1;
       }
@@ -600,7 +621,7 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
     sweeps_used = sweep + 1;
     const int nrot = __ldcg(&a.iscal[TRMPS_I_SVD_ROT + sweep]);
     const float worst = __int_as_float(__ldcg(&a.iscal[TRMPS_I_SVD_ROT + 32 + (sweep & 31)]));
-    if (nrot == 0 || worst < 2e-4f) break;
+    if (nrot == 0 || worst < 1e-3f) break;     // quadratic convergence: what is left is O(worst^2) <= 1e-6
   }
   if (blockIdx.x == 0 && tid == 0) {
     a.iscal[TRMPS_I_SVD_SWEEPS] = sweeps_used;
