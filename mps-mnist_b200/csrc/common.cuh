@@ -151,7 +151,7 @@ int launch_grad(const float* e_near, const float* e_far, const float* phi_near, 
                 int64_t B, int Ds, int L, bool squared, cudaStream_t st);
 int launch_sum_parts(const float* part, int nparts, int64_t n, float* out, cudaStream_t st);
 int launch_grad_tc(const float* e_near, const float* e_far, const float* phi_near, const float* sres, float* gpart, int gsplit,
-                   int64_t B, int Ds, int L, cudaStream_t st);
+                   int64_t B, int Ds, int L, cudaStream_t st, float* dbg = nullptr);
 int grad_tc_splits(int64_t B, int Ds, int L, int sms);
 bool forward_tc_supported(int Ds, int L, int nd);
 int64_t forward_tc_image_floats(int Ds, int L);

@@ -104,15 +104,15 @@ __device__ __forceinline__ uint32_t make_idesc_tf32_mn(int M, int N) {
   return d;
 }
 
+// round-to-nearest (ties away) to TF32 precision with two integer-pipe ops; cvt.rna.tf32.f32 goes through the
+// slow conversion unit and was the bottleneck of the operand producers
 __device__ __forceinline__ float tf32_round(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 struct GradTcArgs {
   const float* e_near; const float* e_far; const float* phi_near; const float* sres; float* gpart;
-  int64_t B, imgs_per_split; int Ds, L, R, Cc;
+  int64_t B, imgs_per_split; int Ds, L, R, Cc; float* dbg;
 };
 
 // byte offset of the 16-byte chunk holding MN elements [mn, mn+4) of image-row k inside a tile whose groups of
@@ -154,57 +154,67 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
   const int cln = vc ? ccol / Ds : 0, ck = vc ? ccol - cln * Ds : 0;
   const uint32_t idesc = make_idesc_tf32_mn(128, TC_TN);
 
-  for (int ch = 0; ch < nch; ++ch) {
-    const int s = ch % TC_STAGES, it = ch / TC_STAGES;
-    uint8_t* st = smem + s * TC_STAGE_BYTES;
-    uint8_t* a_hi = st, *a_lo = st + TC_A_BYTES, *b_hi = st + 2 * TC_A_BYTES, *b_lo = st + 2 * TC_A_BYTES + TC_B_BYTES;
-    // global loads first (they do not touch the stage), then wait until the MMAs that read this stage are done
-    float4 ra[4], rb[4];
+  const bool timer = g.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 32;
+  long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = timer ? clock64() : 0;
+  auto tick = [&](int k) { if (timer) { long long now = clock64(); tacc[k] += now - tprev; tprev = now; } };
+
+  // global -> registers for one chunk: RAW rows of e_near / e_far plus their per-image scale factors for image rows
+  // ksub + 4 r.  Nothing here consumes a loaded value, so all 16 loads of a chunk stay in flight.
+  auto load_chunk = [&](int ch, float4 (&ra)[4], float4 (&rb)[4], float (&pa)[4], float (&pb)[4]) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int64_t t = tbeg + (int64_t)ch * TC_KCH + ksub + 4 * r;
       ra[r] = make_float4(0.f, 0.f, 0.f, 0.f);
       rb[r] = ra[r];
+      pa[r] = 0.f;
+      pb[r] = 0.f;
       if (t < tend) {
         if (va) {
-          float4 v = __ldg(reinterpret_cast<const float4*>(g.e_near + t * Ds + ai));
-          const float p = __ldg(g.phi_near + 2 * t + am);
-          v.x *= p; v.y *= p; v.z *= p; v.w *= p;
-          ra[r] = v;
+          ra[r] = __ldg(reinterpret_cast<const float4*>(g.e_near + t * Ds + ai));
+          pa[r] = __ldg(g.phi_near + 2 * t + am);
         }
         if (vc) {
-          float4 v = __ldg(reinterpret_cast<const float4*>(g.e_far + t * Ds + ck));
-          const float sc = __ldg(g.sres + t * L2 + cln);
-          v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
-          rb[r] = v;
+          rb[r] = __ldg(reinterpret_cast<const float4*>(g.e_far + t * Ds + ck));
+          pb[r] = __ldg(g.sres + t * L2 + cln);
         }
       }
     }
-    if (ch >= TC_STAGES) mbar_wait(&bars[s], (uint32_t)((it - 1) & 1));
+  };
+  // registers -> tf32 hi/lo tiles in stage ch % TC_STAGES, then one thread issues the MMAs of the chunk
+  auto process_chunk = [&](int ch, const float4 (&ra)[4], const float4 (&rb)[4], const float (&pa)[4], const float (&pb)[4]) {
+    const int s = ch % TC_STAGES, it = ch / TC_STAGES;
+    uint8_t* st = smem + s * TC_STAGE_BYTES;
+    uint8_t* a_hi = st, *a_lo = st + TC_A_BYTES, *b_hi = st + 2 * TC_A_BYTES, *b_lo = st + 2 * TC_A_BYTES + TC_B_BYTES;
+    tick(0);
+    if (ch >= TC_STAGES) mbar_wait(&bars[s], (uint32_t)((it - 1) & 1));   // MMAs that read this stage are done
+    tick(1);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int k = ksub + 4 * r;
       {
         float4 hi, lo;
-        hi.x = tf32_round(ra[r].x); hi.y = tf32_round(ra[r].y); hi.z = tf32_round(ra[r].z); hi.w = tf32_round(ra[r].w);
-        lo.x = tf32_round(ra[r].x - hi.x); lo.y = tf32_round(ra[r].y - hi.y);
-        lo.z = tf32_round(ra[r].z - hi.z); lo.w = tf32_round(ra[r].w - hi.w);
+        const float vx = ra[r].x * pa[r], vy = ra[r].y * pa[r], vz = ra[r].z * pa[r], vw = ra[r].w * pa[r];
+        hi.x = tf32_round(vx); hi.y = tf32_round(vy); hi.z = tf32_round(vz); hi.w = tf32_round(vw);
+        lo.x = vx - hi.x; lo.y = vy - hi.y; lo.z = vz - hi.z; lo.w = vw - hi.w;
         const uint32_t off = tile_off(4 * q4, k, TC_TM / 32);
         *reinterpret_cast<float4*>(a_hi + off) = hi;
         *reinterpret_cast<float4*>(a_lo + off) = lo;
       }
       {
         float4 hi, lo;
-        hi.x = tf32_round(rb[r].x); hi.y = tf32_round(rb[r].y); hi.z = tf32_round(rb[r].z); hi.w = tf32_round(rb[r].w);
-        lo.x = tf32_round(rb[r].x - hi.x); lo.y = tf32_round(rb[r].y - hi.y);
-        lo.z = tf32_round(rb[r].z - hi.z); lo.w = tf32_round(rb[r].w - hi.w);
+        const float vx = rb[r].x * pb[r], vy = rb[r].y * pb[r], vz = rb[r].z * pb[r], vw = rb[r].w * pb[r];
+        hi.x = tf32_round(vx); hi.y = tf32_round(vy); hi.z = tf32_round(vz); hi.w = tf32_round(vw);
+        lo.x = vx - hi.x; lo.y = vy - hi.y; lo.z = vz - hi.z; lo.w = vw - hi.w;
         const uint32_t off = tile_off(4 * q4, k, TC_TN / 32);
         *reinterpret_cast<float4*>(b_hi + off) = hi;
         *reinterpret_cast<float4*>(b_lo + off) = lo;
       }
     }
+    tick(2);
     fence_async_proxy();          // make the generic-proxy stores visible to the tensor core (async proxy)
+    tick(3);
     __syncthreads();
+    tick(4);
     if (tid == 0) {
       tc_fence_after();
       const uint32_t acc0 = ch > 0 ? 1u : 0u;
@@ -228,8 +238,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
       umma_commit(&bars[s]);                          // stage s may be overwritten once these MMAs have read it
       if (ch == nch - 1) umma_commit(&bars[TC_STAGES]);
     }
+  };
+
+  // software pipeline: the global loads of chunks ch+1 and ch+2 are in flight while chunk ch is converted and issued
+  {
+    float4 ra0[4], rb0[4], ra1[4], rb1[4];
+    float pa0[4], pb0[4], pa1[4], pb1[4];
+    if (nch > 0) load_chunk(0, ra0, rb0, pa0, pb0);
+    if (nch > 1) load_chunk(1, ra1, rb1, pa1, pb1);
+    for (int ch = 0; ch < nch; ch += 2) {
+      process_chunk(ch, ra0, rb0, pa0, pb0);
+      if (ch + 2 < nch) load_chunk(ch + 2, ra0, rb0, pa0, pb0);
+      if (ch + 1 < nch) {
+        process_chunk(ch + 1, ra1, rb1, pa1, pb1);
+        if (ch + 3 < nch) load_chunk(ch + 3, ra1, rb1, pa1, pb1);
+      }
+    }
   }
 
+  if (timer) for (int k = 0; k < 6; ++k) g.dbg[k] = (float)tacc[k];
   // epilogue: TMEM -> registers -> global partial tile.  Warps 0-3 read accumulator 0, warps 4-7 accumulator 1.
   float* out = g.gpart + (size_t)blockIdx.z * g.R * g.Cc;
   const int mt = warp >> 2, quad = warp & 3;
@@ -273,10 +300,10 @@ int grad_tc_splits(int64_t B, int Ds, int L, int sms) {
 }
 
 int launch_grad_tc(const float* e_near, const float* e_far, const float* phi_near, const float* sres, float* gpart, int gsplit,
-                   int64_t B, int Ds, int L, cudaStream_t st) {
+                   int64_t B, int Ds, int L, cudaStream_t st, float* dbg) {
   GradTcArgs g;
   g.e_near = e_near; g.e_far = e_far; g.phi_near = phi_near; g.sres = sres; g.gpart = gpart;
-  g.B = B; g.Ds = Ds; g.L = L; g.R = 2 * Ds; g.Cc = 2 * L * Ds;
+  g.B = B; g.Ds = Ds; g.L = L; g.R = 2 * Ds; g.Cc = 2 * L * Ds; g.dbg = dbg;
   int64_t per = ceil_div64(B, gsplit);
   g.imgs_per_split = ceil_div64(per, TC_KCH) * TC_KCH;
   static bool attr_set = false;

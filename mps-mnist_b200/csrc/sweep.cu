@@ -230,7 +230,7 @@ static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const Bond
   {
     ProfScope ps(PROF_GRAD, st);
     if (g_grad_impl == 0) {
-      if ((rc = launch_grad_tc(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit_tc, s->B, Ds, L, st))) return rc;
+      if ((rc = launch_grad_tc(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit_tc, s->B, Ds, L, st, getenv("TRMPS_GRAD_DEBUG") ? w + lay.hres : nullptr))) return rc;
       if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit_tc, RC, w + lay.gradM, st))) return rc;
     } else {
       if ((rc = launch_grad(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit, s->B, Ds, L, false, st))) return rc;

@@ -53,6 +53,9 @@ def main():
     t = timed(lambda: st.bond_merge(loc, +1)); print("merge                         min %.3f ms  med %.3f ms" % t)
     t = timed(lambda: st.bond_forward(loc, +1, 0)); print("forward                       min %.3f ms  med %.3f ms   %.1f TFLOP/s" % (*t, flops / t[0] / 1e9))
     t = timed(lambda: st.bond_gradient(loc, +1, opt)); print("forward+loss+gradient         min %.3f ms  med %.3f ms" % t)
+    if os.environ.get("TRMPS_GRAD_DEBUG"):
+        ph = st.work[st.layout.hres:st.layout.hres + 6].cpu().numpy()
+        print("  grad_tc CTA0 warp1 cycles (loads+prev mma issue, wait empty, convert+store, fence, sync, -):", [int(x) for x in ph], "sum", int(ph.sum()))
     st.bond_merge(loc, +1)
     t = timed(lambda: (st.bond_merge(loc, +1), st.bond_split(loc, +1, opt), st.set_nodes(nodes, loc))[0], reps=3, warm=1)
     iw = st.iwork.cpu().numpy()
