@@ -1,0 +1,109 @@
+"""Runs the REFERENCE's own hot-path code (trmps/mps/mps.py, trmps/optimizers/*.py, unmodified, imported from
+/root/reference) under the NumPy TF1 stand-in `oracle/tf1_shim.py` on small seeded inputs and commits what it
+produced as golden vectors:  tests/golden/ref_*.npz.
+
+    python oracle/make_golden_from_reference.py          (only works where /root/reference exists)
+
+Each file holds the inputs (pixels, labels, configuration) and the reference's outputs after
+`MPSOptimizer.train(data_source, batch_size, n_step=1, ...)`: the N updated weight tensors' bond dimensions, the
+logits `MPS.predict` gives with the initial and with the updated weights, and the training cost.  tests/ then check
+(a) the oracle restatement and (b) the CUDA path against these vectors.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference/trmps"
+OUT = os.path.join(HERE, "..", "tests", "golden")
+
+sys.path.insert(0, HERE)
+import tf1_shim
+tf = tf1_shim.install()
+import trmps_oracle as o          # only for the seeded synthetic inputs and the feature map
+
+sys.path.insert(0, REF)
+from optimizers.optimizer import MPSOptimizer                      # noqa: E402  (reference code)
+from optimizers.parameterObjects import MPSOptimizerParameters, MPSTrainingParameters   # noqa: E402
+from mps.mps import MPS                                            # noqa: E402
+from mps.squaredDistanceMPS import sqMPS                           # noqa: E402
+
+CASES = {
+    # name: (N, B, L, max_size, loc, lr, loss, updates_per_step, seed)
+    "ref_xent_n8": (8, 96, 10, 24, None, 0.05, 0, 1, 7),
+    "ref_xent_n10_loc0": (10, 64, 10, 32, 0, 0.05, 0, 1, 8),
+    "ref_squared_n6": (6, 80, 10, 24, 2, 0.02, 1, 2, 9),
+}
+
+
+class FixedBatch(object):
+    """Duck-typed MPSDatasource: one fixed batch, also used as the test set."""
+
+    def __init__(self, phi, labels):
+        self.phi, self.labels = phi, labels
+
+    @property
+    def test_data(self):
+        return self.phi, self.labels
+
+    def next_training_data_batch(self, batch_size):
+        assert batch_size == self.phi.shape[1]
+        return self.phi, self.labels
+
+
+def reference_predict(network, weights, phi):
+    feature = tf.placeholder(tf.float32, shape=[network.input_size, None, network.d_feature])
+    f = network.predict(feature)
+    feed = network.create_feed_dict(weights)
+    feed[feature] = phi
+    with tf.Session() as sess:
+        return sess.run(f, feed_dict=feed)
+
+
+def run_case(N, B, L, max_size, loc, lr, loss, updates, seed):
+    pix, lab = o.synthetic_batch(N, B, L, seed=seed)
+    phi = o.feature_map(pix, o.FM_ONE_SQRT3)
+    cls = sqMPS if loss == 1 else MPS
+    network = cls(2, L, N, special_node_loc=loc)
+    network.prepare()                                   # default linear-model MPS (mps.py:211-219)
+    f_init = reference_predict(network, None, phi)
+    lr_reg = 0.99
+    params = MPSOptimizerParameters(path="/tmp/ref_MPSconfig", updates_per_step=updates, lr_reg=lr_reg)
+    optimizer = MPSOptimizer(network, max_size, params)
+    # train() scales the rate by 1/sqrt(1 - lr_reg^(i+1)) (baseoptimizer.py:109): undo it so that step 0 runs at `lr`
+    rate0 = lr * np.sqrt(1 - lr_reg)
+    optimizer.train(FixedBatch(phi, lab), B, 1, MPSTrainingParameters(rate_of_change=rate0, verbose_save=False))
+    weights = [np.asarray(w) for w in optimizer.test]
+    # after MPSOptimizer.__init__ the network's node graph is the post-sweep graph (baseoptimizer.py:221-238), so
+    # evaluate the updated weights the way a user would: a fresh MPS prepared from them (mps.py:205-206, :425-443)
+    fresh = cls(2, L, N, special_node_loc=int(network._special_node_loc))
+    fresh.prepare(_weights=weights)
+    f_final = reference_predict(fresh, None, phi)
+    with tf.Session() as sess:
+        cost = sess.run(network.cost(tf1_shim.convert_to_tensor(f_final), tf1_shim.convert_to_tensor(lab)))
+    return dict(pixels=pix, labels=lab, loc=np.int32(network._special_node_loc), f_init=f_init, f_final=f_final,
+                cost_final=np.float32(cost), dims=np.array([w.shape[-1] for w in weights]),
+                cfg=np.array([x if x is not None else -1 for x in (N, B, L, max_size, loc, lr, loss, updates, seed)], dtype=np.float64))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, cfg in CASES.items():
+        sink = io.StringIO()
+        with contextlib.redirect_stdout(sink):            # the reference prints a lot
+            rec = run_case(*cfg)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print(name, "dims", rec["dims"].tolist(), "cost", float(rec["cost_final"]))
+
+
+if __name__ == "__main__":
+    # the lazy graph is evaluated recursively and the reference chains thousands of TensorArray writes
+    import threading
+    sys.setrecursionlimit(1000000)
+    threading.stack_size(1 << 30)
+    t = threading.Thread(target=main)
+    t.start()
+    t.join()

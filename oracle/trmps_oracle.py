@@ -6,11 +6,14 @@ BASELINE.json.  It is the checker for the CUDA path, never the product: only
 ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
 legs of ``bench.py`` may import it.
 
-Parity status: the reference holds no golden vectors for this path (its single unit
-test is stale) and TensorFlow 1.2 cannot be installed here.  The
-restatement is pinned instead against the reference's own Python control flow executed
-under a NumPy stand-in for the handful of TF ops it uses (``oracle/tf1_shim.py`` +
-``oracle/make_golden.py``; outputs committed under ``tests/golden/``).
+Parity status: PINNED against the reference's own code.  The reference holds no golden
+vectors for this path (its single unit test is stale) and
+TensorFlow 1.2 cannot be installed here, so the reference's hot-path modules are executed
+UNMODIFIED under a NumPy stand-in for the ~45 TF symbols they use (``oracle/tf1_shim.py``,
+driver ``oracle/make_golden_from_reference.py``); their outputs are committed as
+``tests/golden/ref_*.npz`` and this restatement reproduces them bit for bit
+(``tests/test_oracle.py``).  What is NOT pinned is TensorFlow's own kernels (Eigen
+einsum/tensordot summation order, its SVD): they are replaced by NumPy/LAPACK.
 
 Every function cites the reference file:line it follows (paths relative to the
 reference root).  ``dtype`` is float32 to match the reference graph; pass

@@ -297,7 +297,28 @@ def test_optimizer_class_train_runs_and_learns(tmp_path):
 import glob
 import os
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = [p for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+          if not os.path.basename(p).startswith("ref_")]
+REF_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz")))
+
+
+@pytest.mark.parametrize("path", REF_GOLDEN, ids=[os.path.basename(p) for p in REF_GOLDEN])
+def test_cuda_path_matches_reference_code_vectors(path):
+    """Vectors produced by the REFERENCE's own Python executed under the NumPy TF1 stand-in (oracle/tf1_shim.py)."""
+    g = np.load(path)
+    N, B, L, ms, loc, lr, loss, upd, seed = g['cfg']
+    N, B, L, ms, loss, upd = int(N), int(B), int(L), int(ms), int(loss), int(upd)
+    nodes, loc = o.initial_nodes(N, 2, L, loc=None if loc < 0 else int(loc))
+    st = make_state(N, B, L, ms, nodes, loc, g['pixels'], g['labels'], fm=nat.FM_ONE_SQRT3, loss=loss)
+    assert rel(dev.predict(st.weights_view(), st.feat, nat.FM_ONE_SQRT3).cpu().numpy(), g['f_init']) < 1e-5
+    st.train_step(dev.make_opt(lr=float(lr), max_size=ms, updates_per_step=upd), loc=loc)
+    torch.cuda.synchronize()
+    assert [w.shape[-1] for w in st.get_nodes()] == g['dims'].tolist()          # bond dimensions: exact
+    got = dev.predict(st.weights_view(), st.feat, nat.FM_ONE_SQRT3).cpu().numpy()
+    assert rel(got, g['f_final']) < 3e-3                                        # 2(N-1) chained fp32 updates
+    assert np.mean(got.argmax(1) == g['f_final'].argmax(1)) >= 0.98
+    got_cost = o.cost(got, g['labels'], loss)
+    assert abs(got_cost - float(g['cost_final'])) < 5e-3 * abs(float(g['cost_final']))
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])

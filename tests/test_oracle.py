@@ -8,7 +8,9 @@ import pytest
 
 import trmps_oracle as o
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+ALL_NPZ = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = [p for p in ALL_NPZ if not os.path.basename(p).startswith("ref_")]     # written by oracle/make_golden.py
+REF_GOLDEN = [p for p in ALL_NPZ if os.path.basename(p).startswith("ref_")]     # written by the REFERENCE code under oracle/tf1_shim.py
 
 
 def rel(a, b):
@@ -40,7 +42,45 @@ def test_oracle_reproduces_golden(path):
 
 
 def test_golden_files_present():
-    assert len(GOLDEN) >= 3
+    assert len(GOLDEN) >= 3 and len(REF_GOLDEN) >= 3
+
+
+@pytest.mark.parametrize("path", REF_GOLDEN, ids=[os.path.basename(p) for p in REF_GOLDEN])
+def test_oracle_matches_reference_code_run_under_tf_shim(path):
+    """tests/golden/ref_*.npz were produced by the reference's own trmps/mps/mps.py + trmps/optimizers/*.py executed
+    under the NumPy TF1 stand-in (oracle/make_golden_from_reference.py).  The restatement must reproduce them."""
+    g = np.load(path)
+    N, B, L, ms, loc, lr, loss, upd, seed = golden_cfg(g)
+    pix, lab = o.synthetic_batch(N, B, L, seed=seed)
+    assert np.array_equal(pix, g['pixels']) and np.array_equal(lab, g['labels'])
+    phi = o.feature_map(pix, o.FM_ONE_SQRT3)
+    nodes, loc = o.initial_nodes(N, 2, L, loc=loc)
+    assert loc == int(g['loc'])
+    assert rel(o.predict(nodes, loc, phi, L), g['f_init']) < 1e-6
+    new = o.train_step(nodes, loc, phi, lab, lr, o.SweepParams(max_size=ms, updates_per_step=upd, loss_kind=loss), L)
+    assert [w.shape[-1] for w in new] == g['dims'].tolist()
+    f = o.predict(new, loc, phi, L)
+    assert rel(f, g['f_final']) < 1e-5
+    assert abs(o.cost(f, lab, loss) - float(g['cost_final'])) < 1e-5 * abs(float(g['cost_final']))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/trmps"), reason="reference sources not present on this machine")
+def test_reference_code_runs_under_the_shim_and_reproduces_committed_vectors(tmp_path):
+    import subprocess, sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); sys.setrecursionlimit(1000000); import threading; threading.stack_size(1<<30)\n"
+            "import make_golden_from_reference as m\n"
+            "out = {}\n"
+            "def go():\n"
+            "    import io, contextlib\n"
+            "    with contextlib.redirect_stdout(io.StringIO()):\n"
+            "        out['r'] = m.run_case(*m.CASES['ref_xent_n8'])\n"
+            "t = threading.Thread(target=go); t.start(); t.join()\n"
+            "g = np.load(%r)\n"
+            "assert np.array_equal(out['r']['f_final'], g['f_final']) and np.array_equal(out['r']['dims'], g['dims'])\n"
+            "print('ok')\n") % (os.path.join(root, "oracle"), os.path.join(root, "tests", "golden", "ref_xent_n8.npz"))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stderr[-2000:]
 
 
 def test_initial_mps_is_the_linear_model():
