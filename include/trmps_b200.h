@@ -154,7 +154,7 @@ typedef struct {
 int         trmps_abi_version(void);
 const char* trmps_last_error(void);
 int         trmps_device_check(int device);             /* TRMPS_OK if `device` is an sm_100 GPU */
-int         trmps_set_option(int32_t option, int32_t value); /* option 0: gradient kernel, option 1: forward kernel; value 0 = tcgen05 3xTF32 (default), 1 = FP32 SIMT */
+int         trmps_set_option(int32_t option, int32_t value); /* option 0: gradient kernel, 1: forward kernel, 2: inference chain; value 0 = tcgen05 3xTF32 (default), 1 = FP32 SIMT */
 int64_t     trmps_launch_count(void);                   /* kernels launched by this library so far (process-wide) */
 
 /* optional device-side timing of the kernels a sweep launches (CUDA events on the caller's stream; replaces the

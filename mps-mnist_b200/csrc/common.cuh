@@ -153,6 +153,11 @@ int launch_sum_parts(const float* part, int nparts, int64_t n, float* out, cudaS
 int launch_grad_tc(const float* e_near, const float* e_far, const float* phi_near, const float* sres, float* gpart, int gsplit,
                    int64_t B, int Ds, int L, cudaStream_t st, float* dbg = nullptr);
 int grad_tc_splits(int64_t B, int Ds, int L, int sms);
+bool chain_tc_supported(int Ds);
+int64_t chain_tc_image_floats(int nsteps);
+int launch_chain_tc(const float* feat, int fm, int64_t B, int Ds, int L, const float* nodes, int first, int dir, int nsteps,
+                    int start_kind, float* img, float* out, cudaStream_t st);
+int option_value(int option);
 bool forward_tc_supported(int Ds, int L, int nd);
 int64_t forward_tc_image_floats(int Ds, int L);
 int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_near, const float* phi_far, const float* M,

@@ -288,7 +288,7 @@ extern "C" int trmps_env_step(const float* feat_site, int32_t feature_map, int64
 
 extern "C" int64_t trmps_predict_work_floats(int64_t B, int32_t L, int32_t Ds) {
   // 4 environment buffers, the special-node matrix, phi of the special site, one partial-logit buffer
-  return 4 * B * Ds + (int64_t)2 * Ds * L * Ds + 2 * B + B * L;
+  return 4 * B * Ds + (int64_t)2 * Ds * L * Ds + 2 * B + B * L + 4096 /*alignment*/ + chain_tc_image_floats(1 << 14);
 }
 
 extern "C" int trmps_predict(const trmps_predict_desc* p, void* stream) {
@@ -311,6 +311,17 @@ extern "C" int trmps_predict(const trmps_predict_desc* p, void* stream) {
   float* fpart = phi_loc + 2 * B;
   const size_t slot = (size_t)2 * Ds * Ds;
   int rc;
+  if (option_value(2) == 0 && chain_tc_supported(Ds) && N <= (1 << 14)) {
+    // fused tensor-core chains: the environments never leave the SM between sites
+    float* img = fpart + B * L;
+    img += (4 - ((uintptr_t)img / sizeof(float)) % 4) % 4;
+    if ((rc = launch_chain_tc(p->feat, fm, B, Ds, L, p->nodes, 0, +1, p->loc, 0, img, buf[0], st))) return rc;
+    if ((rc = launch_chain_tc(p->feat, fm, B, Ds, L, p->nodes, N - 1, -1, N - 1 - p->loc, 1, img, buf[2], st))) return rc;
+    if ((rc = launch_special_to_matrix(p->special, M, Ds, L, st))) return rc;
+    if ((rc = trmps::launch_phi_site(p->feat + feat_site_offset(fm, B, p->loc), fm, B, phi_loc, st))) return rc;
+    if ((rc = launch_forward(buf[0], buf[2], phi_loc, nullptr, M, fpart, 1, B, Ds, L, 1, p->dims + p->loc, st))) return rc;
+    return launch_sum_round_logits(fpart, 1, B, L, p->round_output, p->logits, st);
+  }
   // left chain (mps.py:536-541)
   int cur = 0;
   if ((rc = launch_fill_boundary(buf[cur], B, Ds, L, 0, st))) return rc;

@@ -52,6 +52,8 @@ ProfScope::~ProfScope() {
 
 static int g_grad_impl = 0;   // 0 = tcgen05 3xTF32, 1 = FP32 SIMT
 static int g_fwd_impl = 0;    // same for the forward contraction
+static int g_chain_impl = 0;  // 0 = fused tcgen05 chain for inference when Ds <= 32, 1 = per-site FP32 SIMT steps
+int option_value(int option) { return option == 0 ? g_grad_impl : option == 1 ? g_fwd_impl : g_chain_impl; }
 
 static int g_sm_count = 0;
 static int sm_count() {
@@ -381,6 +383,7 @@ extern "C" int64_t trmps_launch_count(void) { return (int64_t)g_launches; }
 extern "C" int trmps_set_option(int32_t option, int32_t value) {
   if (option == 0 && (value == 0 || value == 1)) { g_grad_impl = value; return TRMPS_OK; }
   if (option == 1 && (value == 0 || value == 1)) { g_fwd_impl = value; return TRMPS_OK; }
+  if (option == 2 && (value == 0 || value == 1)) { g_chain_impl = value; return TRMPS_OK; }
   set_error("trmps_set_option: unknown option %d / value %d", option, value);
   return TRMPS_E_ARG;
 }

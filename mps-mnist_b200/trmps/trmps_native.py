@@ -136,6 +136,7 @@ def profile_end():
 
 OPT_GRAD_IMPL, GRAD_TCGEN05, GRAD_SIMT = 0, 0, 1
 OPT_FWD_IMPL, FWD_TCGEN05, FWD_SIMT = 1, 0, 1
+OPT_CHAIN_IMPL, CHAIN_TCGEN05, CHAIN_SIMT = 2, 0, 1
 
 
 def set_option(option, value):

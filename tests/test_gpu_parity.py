@@ -92,7 +92,7 @@ def test_predict_matches_oracle(N, B, D, loc):
     want32 = o.predict(nodes, loc, phi, L)
     want64 = o.predict([n.astype(np.float64) for n in nodes], loc, phi.astype(np.float64), L)
     assert rel(got, want64) < RTOL
-    assert rel(got, want64) < 10 * max(rel(want32, want64), 1e-7)
+    assert rel(got, want64) < max(50 * rel(want32, want64), 2e-5)      # 3xTF32 chain: ~1e-6 per site, well inside 1e-4
     margin = np.sort(want64, axis=1)
     clear = (margin[:, -1] - margin[:, -2]) > 1e-5 * np.abs(margin[:, -1])
     assert np.array_equal(got.argmax(1)[clear], want64.argmax(1)[clear])      # argmax bit-exact
@@ -411,3 +411,23 @@ def test_tcgen05_forward_matches_simt_and_fp64(D, B, direction):
     assert rel(results[nat.FWD_SIMT], f64) < 1e-5
     assert rel(results[nat.FWD_TCGEN05], f64) < 1e-5
     assert np.array_equal(results[nat.FWD_TCGEN05].argmax(1), f64.argmax(1)) or rel(results[nat.FWD_TCGEN05], f64) < 1e-6
+
+
+@pytest.mark.parametrize("N,B,D,loc", [(16, 333, None, None), (40, 1500, 32, 13), (24, 700, 32, 0), (24, 700, 24, 23)])
+def test_fused_tcgen05_chain_matches_simt_and_fp64(N, B, D, loc):
+    L = 10
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=81, fm=o.FM_COS_SIN, full_bond=D, loc=loc)
+    w = dev.DeviceWeights(nodes, loc, L, dev.bond_stride(nodes, loc, L), cuda())
+    res = {}
+    try:
+        for impl in (nat.CHAIN_SIMT, nat.CHAIN_TCGEN05):
+            nat.set_option(nat.OPT_CHAIN_IMPL, impl)
+            res[impl] = dev.predict(w, torch.from_numpy(pix).cuda(), nat.FM_COS_SIN).cpu().numpy()
+    finally:
+        nat.set_option(nat.OPT_CHAIN_IMPL, nat.CHAIN_TCGEN05)
+    want = o.predict([n.astype(np.float64) for n in nodes], loc, phi.astype(np.float64), L)
+    assert rel(res[nat.CHAIN_SIMT], want) < 1e-5
+    assert rel(res[nat.CHAIN_TCGEN05], want) < 2e-5
+    margin = np.sort(want, axis=1)
+    clear = (margin[:, -1] - margin[:, -2]) > 1e-4 * np.abs(margin[:, -1])
+    assert np.array_equal(res[nat.CHAIN_TCGEN05].argmax(1)[clear], want.argmax(1)[clear])

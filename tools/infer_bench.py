@@ -1,0 +1,27 @@
+"""Inference throughput at cfg5 (N=784, D=32, B images): MPS.predict on raw pixels with the fused cos/sin feature map."""
+import os, sys, time
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(ROOT, "mps-mnist_b200", "trmps")); sys.path.insert(0, ROOT)
+import numpy as np, torch
+import trmps_native as nat, trmps_device as dev
+from bench import full_bond_mps
+N, D, L = 784, 32, 10
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+loc = N // 2
+nodes = full_bond_mps(N, 2, L, D, loc)
+w = dev.DeviceWeights(nodes, loc, L, dev.bond_stride(nodes, loc, L), torch.device("cuda", 0))
+g = torch.Generator(device="cuda").manual_seed(0)
+pix = torch.rand((N, B), device="cuda", generator=g)
+out = torch.empty((B, L), device="cuda")
+for _ in range(2):
+    dev.predict(w, pix, nat.FM_COS_SIN, out=out)
+torch.cuda.synchronize()
+ts = []
+for _ in range(3):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); dev.predict(w, pix, nat.FM_COS_SIN, out=out); b.record(); torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+ms = min(ts)
+flops = B * ((N - 1) * 2.0 * 2 * D * D + 2.0 * L * 2 * D * D)
+print("predict N=%d D=%d B=%d: %.2f ms  -> %.2f M images/s, %.1f TFLOP/s algorithmic, pixel stream %.0f GB/s; logits mean %.4f" %
+      (N, D, B, ms, B / ms / 1e3, flops / ms / 1e9, 4.0 * N * B / ms / 1e6, float(out.mean())))
