@@ -12,6 +12,8 @@ Jacobi SVD split, environment advance) including the initial environment build.
 Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -347,6 +349,8 @@ def run_ours(args, rank, local_rank, world):
 
 
 def main():
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: the contract is ONE JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -367,10 +371,25 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank)
-    else:
-        run_ours(args, rank, local_rank, world)
+    # Everything libraries print (NCCL banners, reference-style progress prints) goes to stderr; stdout carries
+    # exactly one JSON line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    captured = io.StringIO()
+    with contextlib.redirect_stdout(captured):
+        if args.impl == "reference":
+            run_reference(args, rank)
+        else:
+            run_ours(args, rank, local_rank, world)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    lines = [l for l in captured.getvalue().splitlines() if l.startswith("{")]
+    for l in captured.getvalue().splitlines():
+        if not l.startswith("{"):
+            print(l, file=sys.stderr)
+    if lines:
+        os.write(1, (lines[-1] + "\n").encode())
 
 
 if __name__ == "__main__":
