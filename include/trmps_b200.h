@@ -161,6 +161,7 @@ int64_t     trmps_launch_count(void);                   /* kernels launched by t
  * tf.RunOptions(FULL_TRACE) timeline of baseoptimizer.py:82-86).  Categories: 0 env chain, 1 forward contraction,
  * 2 gradient contraction, 3 SVD split, 4 bond merge, 5 scalar/elementwise, 6 all-reduce. */
 #define TRMPS_PROF_NCAT 7
+int trmps_debug_chain(float* out16);   /* development aid: phase cycle counters of the last fused-chain launch */
 int trmps_profile_begin(int32_t max_records);
 int trmps_profile_end(float* ms_per_cat, int32_t* count_per_cat, int32_t ncat);   /* synchronises the recorded events */
 

@@ -116,6 +116,8 @@ __global__ void chain_prep_kernel(const float* __restrict__ nodes, float* __rest
   }
 }
 
+__device__ float g_chain_dbg[16];
+
 struct ChainArgs {
   const float* feat; int fm; int64_t B; int Ds, L; int first, dir, nsteps; int start_kind;   // start_kind 0: [0_L,1_L], 1: [1_L,0_L]
   const float* img; float* out;      // out: (B, Ds) final environment
@@ -158,13 +160,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(ChainArgs a) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)((2 * CH_KP) >> 3) << 17) | ((uint32_t)(CH_TM >> 4) << 24);
+      const bool itimer = blockIdx.x == 0;
+      long long iacc[3] = {0, 0, 0}, iprev = clock64();
+      auto itick = [&](int q) { if (itimer) { long long now = clock64(); iacc[q] += now - iprev; iprev = now; } };
       for (int s = 0; s < nsteps; ++s) {
         const int st = s % CH_NSTAGE;
         mbar_wait(&node_full[st], (uint32_t)((s / CH_NSTAGE) & 1));
+        itick(0);
         const uint32_t bh = smem_u32(n_base + st * 2 * CH_IMG_BYTES), bl = bh + CH_IMG_BYTES;
         for (int k = 0; k < CH_TILES; ++k) {
           mbar_wait(&a_ready[k], (uint32_t)(s & 1));
           tc_fence_after();
+          itick(1);
           const uint32_t ah = smem_u32(a_base + k * 2 * CH_A_BYTES), al = ah + CH_A_BYTES;
           const uint32_t d = tmem_base + k * 2 * CH_KP;
 #pragma unroll
@@ -177,9 +184,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(ChainArgs a) {
             umma_tf32(d, dah, dbl, idesc, 1u);
           }
           umma_commit(&x_ready[k]);
+          itick(2);
         }
         umma_commit(&node_empty[st]);
       }
+      if (itimer) for (int q = 0; q < 3; ++q) g_chain_dbg[4 + q] = (float)iacc[q];
     }
   } else {
     // ===== epilogue warpgroup of tile k: one image row per thread =====
@@ -210,13 +219,31 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(ChainArgs a) {
       mbar_arrive(&a_ready[k]);
     };
     if (nsteps > 0) store_state();
-    float2 ph = make_float2(0.f, 0.f);
-    if (nsteps > 0 && live) ph = load_phi(a.feat + feat_site_offset(a.fm, a.B, a.first), a.fm, t);
+    const bool timer = blockIdx.x == 0 && tid == 0;
+    long long tacc[4] = {0, 0, 0, 0}, tprev = timer ? clock64() : 0;
+    auto tick = [&](int q) { if (timer) { long long now = clock64(); tacc[q] += now - tprev; tprev = now; } };
+    // raw feature of a site for my image: pixel (in .x) or the precomputed phi; fetched TWO sites ahead so that the
+    // load latency never meets the sincos that consumes it
+    auto load_raw = [&](int step) -> float2 {
+      if (!live || step >= nsteps) return make_float2(0.f, 0.f);
+      const float* fs = a.feat + feat_site_offset(a.fm, a.B, a.first + step * a.dir);
+      if (a.fm == TRMPS_FM_PRECOMPUTED) return __ldg(reinterpret_cast<const float2*>(fs) + t);
+      return make_float2(__ldg(fs + t), 0.f);
+    };
+    auto phi_of_raw = [&](float2 raw) -> float2 {
+      if (!live) return make_float2(0.f, 0.f);
+      return a.fm == TRMPS_FM_PRECOMPUTED ? raw : phi_of_pixel(raw.x, a.fm);
+    };
+    float2 ph = phi_of_raw(load_raw(0));
+    float2 raw1 = load_raw(1);
     for (int s = 0; s < nsteps; ++s) {
-      float2 ph_next = make_float2(0.f, 0.f);
-      if (s + 1 < nsteps && live) ph_next = load_phi(a.feat + feat_site_offset(a.fm, a.B, a.first + (s + 1) * a.dir), a.fm, t);
+      const float2 raw2 = load_raw(s + 2);          // in flight for two steps
+      const float2 ph_next = phi_of_raw(raw1);      // loaded one step ago
+      raw1 = raw2;
+      tick(0);
       mbar_wait(&x_ready[k], (uint32_t)(s & 1));
       tc_fence_after();
+      tick(1);
       float x0[32], x1[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(k * 2 * CH_KP);
       tmem_ld32(taddr, x0);
@@ -224,8 +251,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(ChainArgs a) {
 #pragma unroll
       for (int j = 0; j < CH_KP; ++j) snew[j] = fmaf(ph.x, x0[j], ph.y * x1[j]);
       ph = ph_next;
+      tick(2);
       if (s + 1 < nsteps) store_state();
+      tick(3);
     }
+    if (timer) for (int q = 0; q < 4; ++q) g_chain_dbg[q] = (float)tacc[q];
     if (live) {
       float* o = a.out + t * a.Ds;
       for (int j = 0; j < a.Ds; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(snew[j], snew[j + 1], snew[j + 2], snew[j + 3]);
@@ -239,6 +269,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(ChainArgs a) {
 }  // namespace
 
 bool chain_tc_supported(int Ds) { return Ds <= CH_KP && Ds % 4 == 0; }
+int chain_tc_debug(float* out16) { return cudaMemcpyFromSymbol(out16, g_chain_dbg, 16 * sizeof(float)) == cudaSuccess ? 0 : -1; }
 int64_t chain_tc_image_floats(int nsteps) { return (int64_t)nsteps * 2 * CH_KP * 2 * CH_KP; }
 
 // runs `nsteps` chain steps starting at site `first` in direction dir from the boundary vector; writes the final

@@ -154,6 +154,7 @@ int launch_grad_tc(const float* e_near, const float* e_far, const float* phi_nea
                    int64_t B, int Ds, int L, cudaStream_t st, float* dbg = nullptr);
 int grad_tc_splits(int64_t B, int Ds, int L, int sms);
 bool chain_tc_supported(int Ds);
+int chain_tc_debug(float* out16);
 int64_t chain_tc_image_floats(int nsteps);
 int launch_chain_tc(const float* feat, int fm, int64_t B, int Ds, int L, const float* nodes, int first, int dir, int nsteps,
                     int start_kind, float* img, float* out, cudaStream_t st);

@@ -286,6 +286,8 @@ extern "C" int trmps_env_step(const float* feat_site, int32_t feature_map, int64
   return launch_env_step(feat_site, feature_map, B, Ds, dir, in_env, node_slot, din_dev, out_env, (cudaStream_t)stream);
 }
 
+extern "C" int trmps_debug_chain(float* out16) { return trmps::chain_tc_debug(out16); }
+
 extern "C" int64_t trmps_predict_work_floats(int64_t B, int32_t L, int32_t Ds) {
   // 4 environment buffers, the special-node matrix, phi of the special site, one partial-logit buffer
   return 4 * B * Ds + (int64_t)2 * Ds * L * Ds + 2 * B + B * L + 4096 /*alignment*/ + chain_tc_image_floats(1 << 14);

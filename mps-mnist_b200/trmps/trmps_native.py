@@ -58,6 +58,7 @@ _SIGNATURES = {
     "trmps_device_check": (C.c_int, [C.c_int]),
     "trmps_set_option": (C.c_int, [C.c_int32, C.c_int32]),
     "trmps_launch_count": (C.c_int64, []),
+    "trmps_debug_chain": (C.c_int, [C.POINTER(C.c_float)]),
     "trmps_profile_begin": (C.c_int, [C.c_int32]),
     "trmps_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]),
     "trmps_sweep_layout": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Layout)]),
