@@ -161,13 +161,13 @@ int64_t     trmps_launch_count(void);                   /* kernels launched by t
  * tf.RunOptions(FULL_TRACE) timeline of baseoptimizer.py:82-86).  Categories: 0 env chain, 1 forward contraction,
  * 2 gradient contraction, 3 SVD split, 4 bond merge, 5 scalar/elementwise, 6 all-reduce. */
 #define TRMPS_PROF_NCAT 7
-int trmps_debug_chain(float* out16);   /* development aid: phase cycle counters of the last fused-chain launch */
+int trmps_debug_chain(float* out64);   /* development aid: phase cycle counters of the last fused-chain launch */
 int trmps_profile_begin(int32_t max_records);
 int trmps_profile_end(float* ms_per_cat, int32_t* count_per_cat, int32_t ncat);   /* synchronises the recorded events */
 
 /* sizes */
 int     trmps_sweep_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, int32_t sm_count, trmps_layout* out);
-int64_t trmps_predict_work_floats(int64_t B, int32_t L, int32_t Ds);
+int64_t trmps_predict_work_floats(int64_t B, int32_t L, int32_t Ds, int32_t N);
 
 /* phi = feature_map(pixels): the datasource-side map, MNISTpreprocessing.py:55.  out (N*B, 2). */
 int trmps_feature_map(const float* pixels, int64_t count, int32_t feature_map, float* phi_out, void* stream);

@@ -2,30 +2,75 @@
 // Replaces the loops of MPS.predict (mps.py:536-549: tf.while_loop over _chain_multiply_r / _chain_multiply_l),
 // which the reference runs one site at a time with a (B x D x D) intermediate in memory.
 //
-// One CTA carries 4 tiles of 128 images through ALL sites of a chain without touching HBM except for the pixel
-// stream: per site and tile
-//     X[t,(m,j)] = sum_i S[t,i] * node[m,i,j]        tcgen05.mma, M=128, K=KP, N=2*KP, 3xTF32, accumulator in TMEM
+// One CTA carries TILES tiles of 128 images through ALL sites of a chain without touching HBM except for the
+// pixel stream: per site and tile
+//     X[t,(m,j)] = sum_i S[t,i] * node[m,i,j]        tcgen05.mma kind::f16, M=128, K=KP, N=2*KP, accumulator in TMEM
 //     S'[t,j]    = phi_0(x_t) X[t,(0,j)] + phi_1(x_t) X[t,(1,j)]      epilogue in registers (feature map fused)
-// and S' is re-split into TF32 hi/lo and written straight back into the K-major SWIZZLE_128B shared-memory tile
-// that is the A operand of the next site.  The four tiles are staggered: while the tensor core works on one tile,
-// the epilogue warpgroups of the others drain TMEM and rebuild their A tiles.  Node matrices (pre-split hi/lo
-// images built once per call, L2 resident) are streamed by one warp with cp.async.bulk through an mbarrier ring.
+// and S' goes straight back into the K-major SWIZZLE_128B shared-memory tile that is the A operand of the next site.
 //
-// Warp roles (576 threads): warpgroups 0-3 = epilogue of tile 0-3, warp 16 = MMA issuer, warp 17 = node loader.
+// FP32 emulation on the fp16 pipe (twice the TF32 rate).  Both operands are carried as hi + lo halves,
+//     x = 2^e (h + l),  h = fp16(x 2^-e),  l = fp16(x 2^-e - h),
+// and the product keeps  h.h + l.h + h.l  (the dropped l.l term is 2^-22 relative, the representation error of
+// h + l is 2^-23): the same accuracy as 3xTF32.  fp16's narrow exponent is handled by exact power-of-two scaling:
+// every image row of S carries its own integer exponent, every node matrix one exponent for the site (maximum in
+// [2^13, 2^14)).  The row exponent of a step is PREDICTED from the growth seen in the previous step so that the
+// epilogue converts in a single pass over TMEM; the realised row maximum is checked against a safe window
+// (2^-2 .. 2^15: no overflow, error floor below 2^-23 of the row maximum) and the step is redone with the exact
+// exponent in the rare case it falls outside; the exponents are added back in fp32 only when the final environment is written.
+//
+// Shapes: KP = 32 / 64 / 128 (padded bond), TILES = 4 / 4 / 2 image tiles per CTA (TMEM columns 2*KP*TILES <= 512).
+// The tiles are staggered: while the tensor core works on one tile, the epilogue warpgroups of the others drain
+// TMEM and rebuild their A tiles.  Node images (pre-split fp16 hi/lo, built once per call, L2 resident) are
+// streamed in 128-byte-row pieces by one warp with cp.async.bulk through an mbarrier ring.
+//
+// Warp roles: warpgroup k = epilogue of tile k (one image row per thread), then one MMA-issuer warp and one
+// node-loader warp.
+#include <cuda_fp16.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace trmps {
 
 namespace {
 
-constexpr int CH_KP = 32;                    // padded bond (K of the per-site GEMM); N = 2*KP
-constexpr int CH_TILES = 4;                  // image tiles per CTA
 constexpr int CH_TM = 128;
-constexpr int CH_THREADS = CH_TILES * 128 + 64;
-constexpr int CH_NSTAGE = 4;                 // node-image ring
-constexpr int CH_A_BYTES = CH_TM * CH_KP * 4;            // 16 KB per (hi | lo)
-constexpr int CH_IMG_BYTES = CH_KP * 2 * CH_KP * 4;      // 8 KB per (hi | lo)
-constexpr int CH_SMEM = CH_TILES * 2 * CH_A_BYTES + CH_NSTAGE * 2 * CH_IMG_BYTES + 512 + 1024;
+constexpr int CH_TEXP = 13;                  // node maxima are scaled into [2^13, 2^14)
+constexpr int CH_TROW = 8;                   // image rows aim at a maximum in [2^8, 2^9); accepted window 2^-2 .. 2^15
+
+template <int KP> struct ChainCfg;
+// TILES image tiles per CTA, WG epilogue warpgroups per tile (each owns KP/WG state columns of every row), NSTAGE
+// ring stages of one piece each, PIECES pieces per site.  TILE_MAJOR: a tile runs through all pieces of a site
+// before the next tile starts (needs the ring to hold a whole site); otherwise the tiles alternate on each piece.
+template <> struct ChainCfg<32> {
+  static constexpr int TILES = 4, WG = 1, NSTAGE = 4, PIECES = 1;
+  static constexpr bool TILE_MAJOR = true;
+  static constexpr int A_BYTES = 16384;                 // one atom column: row = [hi(32) | lo(32)] fp16
+  static constexpr int PIECE_BYTES = 64 * 128;          // 64 rows (m,j), row = [hi(k 0..31) | lo(k 0..31)]
+};
+template <> struct ChainCfg<64> {
+  static constexpr int TILES = 4, WG = 1, NSTAGE = 4, PIECES = 2;  // pieces: hi, lo
+  static constexpr bool TILE_MAJOR = true;
+  static constexpr int A_BYTES = 2 * 16384;             // [hi | lo] x one 64-wide k atom
+  static constexpr int PIECE_BYTES = 128 * 128;
+};
+template <> struct ChainCfg<128> {
+  // N = 256 per MMA: M=128 MMAs with smaller N are bound by the shared-memory operand fetch (8 KB per 64 cycles),
+  // at N = 256 the tensor pipe itself is the limit.  Two warpgroups per tile halve the epilogue latency.
+  static constexpr int TILES = 2, WG = 2, NSTAGE = 3, PIECES = 4;  // pieces: (ka0,hi) (ka0,lo) (ka1,hi) (ka1,lo)
+  static constexpr bool TILE_MAJOR = false;
+  static constexpr int A_BYTES = 4 * 16384;             // [hi ka0 | hi ka1 | lo ka0 | lo ka1]
+  static constexpr int PIECE_BYTES = 256 * 128;
+};
+template <int KP> constexpr int chain_threads() { return ChainCfg<KP>::TILES * ChainCfg<KP>::WG * 128 + 64; }
+constexpr int CH_AUX_BYTES = 256 + 2048;     // barriers + TMEM slot + clock base, then the row-maximum exchange
+constexpr int CH_SMEM_MAX = 232448;          // 227 KB opt-in limit per CTA
+template <int KP> __host__ __device__ constexpr int chain_smem() {
+  // the operand tiles need 1024-byte alignment; ask for as much slack as fits (the dynamic window starts 1024-aligned
+  // when the kernel has no static shared memory, which the kernel checks)
+  constexpr int need = ChainCfg<KP>::TILES * ChainCfg<KP>::A_BYTES + ChainCfg<KP>::NSTAGE * ChainCfg<KP>::PIECE_BYTES + CH_AUX_BYTES;
+  return need + (CH_SMEM_MAX - need < 1024 ? CH_SMEM_MAX - need : 1024);
+}
+template <int KP> constexpr int site_bytes() { return ChainCfg<KP>::PIECES * ChainCfg<KP>::PIECE_BYTES; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -59,15 +104,15 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// 32 consecutive accumulator columns of my TMEM lane (issue only; pair with tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -77,153 +122,298 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ float tf32_round(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B descriptor: 128-byte rows, 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout << 61;
+  d |= (uint64_t)1 << 16;                    // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // SBO
+  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
   return d;
 }
-// B image (MN-major SWIZZLE_128B_BASE32B), N = 2*KP columns, KP rows (k): byte offset of element (col, k)
-__host__ __device__ __forceinline__ uint32_t node_img_off(int col, int k) {
-  const int blk = col >> 5, c32 = (col & 31) >> 3, e = col & 7, kg = k >> 2, k4 = k & 3;
-  return (uint32_t)((kg * (2 * CH_KP / 32) + blk) * 512 + k4 * 128 + ((c32 ^ k4) << 5) + e * 4);
+// byte offset of the 16-byte chunk `ch` (8 fp16 k-values) of row `r` inside a 128-byte-row K-major SWIZZLE_128B block
+__host__ __device__ __forceinline__ uint32_t k128_chunk_off(int r, int ch) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((ch ^ r) & 7) << 4));
+}
+__device__ __forceinline__ float pow2f(int e) { return __int_as_float((e + 127) << 23); }     // -126 <= e <= 127
+__device__ __forceinline__ int exponent_of(float x) { return (int)((__float_as_uint(x) >> 23) & 0xffu) - 127; }
+// x * 2^e for any e (two exact steps keep the intermediate factors in range)
+__device__ __forceinline__ float scale_pow2(float x, int e) {
+  e = max(-250, min(250, e));
+  const int e1 = e / 2;
+  return x * pow2f(e1) * pow2f(e - e1);
 }
 
-// node slots -> hi/lo B images in chain order.  step s uses site first + s*dir.
-//   dir=+1: W[i][(m,j)] = node[m][i][j]     dir=-1: W[j][(m,i)] = node[m][i][j]
-__global__ void chain_prep_kernel(const float* __restrict__ nodes, float* __restrict__ img, int Ds, int first, int dir, int nsteps) {
-  constexpr int PER = CH_KP * 2 * CH_KP;      // elements per (hi | lo) image
-  const int64_t total = (int64_t)nsteps * PER;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int s = (int)(e / PER), r = (int)(e % PER);
-    const int k = r / (2 * CH_KP), col = r % (2 * CH_KP), m = col / CH_KP, n = col % CH_KP;
-    const float* node = nodes + (size_t)(first + s * dir) * 2 * Ds * Ds;
-    float v = 0.f;
-    if (k < Ds && n < Ds) v = dir > 0 ? node[((size_t)m * Ds + k) * Ds + n] : node[((size_t)m * Ds + n) * Ds + k];
-    const float hi = tf32_round(v), lo = v - hi;
-    float* base = img + (size_t)s * 2 * PER;
-    const uint32_t off = node_img_off(col, k) >> 2;
-    base[off] = hi;
-    base[PER + off] = lo;
+// ---- node slots -> scaled fp16 hi/lo images in chain order.  step s uses site first + s*dir.
+//   dir=+1: W[k=i][(m,j)] = node[m][i][j]     dir=-1: W[k=j][(m,i)] = node[m][i][j]
+// exps[s] = e_s - TEXP where 2^e_s <= max|node_s| < 2^(e_s+1): the image holds node * 2^-exps[s].
+__global__ void chain_exp_kernel(const float* __restrict__ nodes, int32_t* __restrict__ exps, int Ds, int first, int dir) {
+  __shared__ float red[32];
+  const int s = blockIdx.x;
+  const float* node = nodes + (size_t)(first + s * dir) * 2 * Ds * Ds;
+  float m = 0.f;
+  for (int e = threadIdx.x; e < 2 * Ds * Ds; e += blockDim.x) m = fmaxf(m, fabsf(node[e]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    exps[s] = (m > 0.f && m < 3.0e38f) ? exponent_of(m) - CH_TEXP : 0;
   }
 }
 
-__device__ float g_chain_dbg[16];
+template <int KP>
+__global__ void chain_prep_kernel(const float* __restrict__ nodes, uint8_t* __restrict__ img, const int32_t* __restrict__ exps,
+                                  int Ds, int first, int dir, int nsteps) {
+  using C = ChainCfg<KP>;
+  constexpr int PER = 2 * KP * (KP / 8);     // (row n, 8-wide k chunk) pairs per site
+  const int64_t total = (int64_t)nsteps * PER;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(e / PER), r = (int)(e % PER);
+    const int n = r / (KP / 8), kc = r % (KP / 8), m = n / KP, j = n % KP;
+    const float* node = nodes + (size_t)(first + s * dir) * 2 * Ds * Ds;
+    const int ex = -exps[s];
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int k = kc * 8 + q;
+      float v = 0.f;
+      if (k < Ds && j < Ds) v = dir > 0 ? node[((size_t)m * Ds + k) * Ds + j] : node[((size_t)m * Ds + j) * Ds + k];
+      v = scale_pow2(v, ex);
+      hi[q] = __float2half_rn(v);
+      lo[q] = __float2half_rn(v - __half2float(hi[q]));
+    }
+    uint8_t* base = img + (size_t)s * (C::PIECES * C::PIECE_BYTES);
+    uint8_t *ph, *pl;
+    if (KP == 32) {          // one piece, row = [hi | lo]
+      ph = base + k128_chunk_off(n, kc);
+      pl = base + k128_chunk_off(n, 4 + kc);
+    } else {                 // pieces (ka, hi), (ka, lo)
+      const int ka = kc >> 3, ch = kc & 7;
+      ph = base + (size_t)(2 * ka) * C::PIECE_BYTES + k128_chunk_off(n, ch);
+      pl = base + (size_t)(2 * ka + 1) * C::PIECE_BYTES + k128_chunk_off(n, ch);
+    }
+    *reinterpret_cast<uint4*>(ph) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(pl) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+__device__ float g_chain_dbg[64];     // [0..7] phase counters, [16..63] event timestamps of the middle step (cycles since kernel start)
 
 struct ChainArgs {
   const float* feat; int fm; int64_t B; int Ds, L; int first, dir, nsteps; int start_kind;   // start_kind 0: [0_L,1_L], 1: [1_L,0_L]
-  const float* img; float* out;      // out: (B, Ds) final environment
+  const uint8_t* img; const int32_t* exps; float* out;      // out: (B, Ds) final environment
+  int dbg;       // development: 1 = epilogue skips TMEM reads and A-tile stores, 2 = loader skips the copies (rate experiments; results invalid)
 };
 
-__global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(ChainArgs a) {
+template <int KP>
+__global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainArgs a) {
+  using C = ChainCfg<KP>;
+  constexpr int TILES = C::TILES, WG = C::WG, NSTAGE = C::NSTAGE, PIECES = C::PIECES, NCOL = 2 * KP, JW = KP / WG;
+  constexpr int EPI_WARPS = TILES * WG * 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_base = smem;                                              // [tile][hi|lo][16 KB]
-  uint8_t* n_base = smem + CH_TILES * 2 * CH_A_BYTES;                  // [stage][hi|lo][8 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(n_base + CH_NSTAGE * 2 * CH_IMG_BYTES);
-  uint64_t* node_full = bars, *node_empty = bars + CH_NSTAGE, *a_ready = bars + 2 * CH_NSTAGE, *x_ready = bars + 2 * CH_NSTAGE + CH_TILES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CH_NSTAGE + 2 * CH_TILES);
+  uint8_t* a_base = smem;                                   // [tile][A_BYTES]
+  uint8_t* n_base = smem + TILES * C::A_BYTES;              // [stage][PIECE_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(n_base + NSTAGE * C::PIECE_BYTES);
+  uint64_t* node_full = bars, *node_empty = bars + NSTAGE, *a_ready = bars + 2 * NSTAGE, *x_ready = bars + 2 * NSTAGE + TILES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * TILES);
+  long long& t_base = *reinterpret_cast<long long*>(bars + 2 * NSTAGE + 2 * TILES + 1);
+  float* mx_x = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [tile][wg][row] partial row maxima
+  static_assert((2 * NSTAGE + 2 * TILES + 2) * 8 <= 256 && TILES * WG * CH_TM * 4 <= 2048, "aux region");
+  constexpr int SMEM_TOTAL = chain_smem<KP>();
+  if (reinterpret_cast<uint8_t*>(bars) + CH_AUX_BYTES > smem_raw + SMEM_TOTAL) __trap();      // alignment slack exhausted
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nsteps = a.nsteps;
 
   if (tid == 0) {
-    for (int s = 0; s < CH_NSTAGE; ++s) { mbar_init(&node_full[s], 1); mbar_init(&node_empty[s], 1); }
-    for (int k = 0; k < CH_TILES; ++k) { mbar_init(&a_ready[k], 128); mbar_init(&x_ready[k], 1); }
+    t_base = clock64();
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&node_full[s], 1); mbar_init(&node_empty[s], 1); }
+    for (int k = 0; k < TILES; ++k) { mbar_init(&a_ready[k], WG * 128); mbar_init(&x_ready[k], 1); }
     fence_barrier_init();
   }
   __syncwarp();
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 0) tmem_alloc(tmem_slot, TILES * NCOL);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == CH_TILES * 4 + 1) {
-    // ===== node loader =====
+  if (warp == EPI_WARPS + 1) {
+    // ===== node loader: one bulk copy per piece =====
     if (lane == 0) {
-      for (int s = 0; s < nsteps; ++s) {
-        const int st = s % CH_NSTAGE;
-        if (s >= CH_NSTAGE) mbar_wait(&node_empty[st], (uint32_t)(((s / CH_NSTAGE) - 1) & 1));
-        mbar_expect_tx(&node_full[st], 2 * CH_IMG_BYTES);
-        bulk_g2s(n_base + st * 2 * CH_IMG_BYTES, a.img + (size_t)s * (2 * CH_IMG_BYTES / 4), 2 * CH_IMG_BYTES, &node_full[st]);
+      const int npieces = nsteps * PIECES;
+      for (int p = 0; p < npieces; ++p) {
+        const int st = p % NSTAGE;
+        if (p >= NSTAGE) mbar_wait(&node_empty[st], (uint32_t)(((p / NSTAGE) - 1) & 1));
+        if (a.dbg == 2) { mbar_arrive(&node_full[st]); continue; }      // experiment: no node traffic (results invalid)
+        mbar_expect_tx(&node_full[st], C::PIECE_BYTES);
+        bulk_g2s(n_base + st * C::PIECE_BYTES, a.img + (size_t)p * C::PIECE_BYTES, C::PIECE_BYTES, &node_full[st]);
       }
     }
-  } else if (warp == CH_TILES * 4) {
+  } else if (warp == EPI_WARPS) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)((2 * CH_KP) >> 3) << 17) | ((uint32_t)(CH_TM >> 4) << 24);
+      // kind::f16: fp16 x fp16 -> fp32, both operands K-major, N = 2*KP, M = 128
+      const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(CH_TM >> 4) << 24);
+      const uint64_t adesc0 = make_desc_k128(smem_u32(a_base)), bdesc0 = make_desc_k128(smem_u32(n_base));
       const bool itimer = blockIdx.x == 0;
       long long iacc[3] = {0, 0, 0}, iprev = clock64();
       auto itick = [&](int q) { if (itimer) { long long now = clock64(); iacc[q] += now - iprev; iprev = now; } };
-      for (int s = 0; s < nsteps; ++s) {
-        const int st = s % CH_NSTAGE;
-        mbar_wait(&node_full[st], (uint32_t)((s / CH_NSTAGE) & 1));
-        itick(0);
-        const uint32_t bh = smem_u32(n_base + st * 2 * CH_IMG_BYTES), bl = bh + CH_IMG_BYTES;
-        for (int k = 0; k < CH_TILES; ++k) {
-          mbar_wait(&a_ready[k], (uint32_t)(s & 1));
-          tc_fence_after();
-          itick(1);
-          const uint32_t ah = smem_u32(a_base + k * 2 * CH_A_BYTES), al = ah + CH_A_BYTES;
-          const uint32_t d = tmem_base + k * 2 * CH_KP;
+      // MMAs of (tile k, piece p of the site).  descriptor start addresses count 16-byte units: +2 per K=16 step
+      // inside an atom, +1024 per 16 KB atom
+      auto issue = [&](int k, int p, uint32_t st) {
+        const uint32_t d = tmem_base + k * NCOL;
+        const uint64_t ad = adesc0 + (uint64_t)(k * (C::A_BYTES >> 4));
+        const uint64_t bd = bdesc0 + (uint64_t)(st * (C::PIECE_BYTES >> 4));
+        if (KP == 32) {
+          umma_f16(d, ad + 0, bd + 0, idesc, 0u);          // hi . hi
+          umma_f16(d, ad + 2, bd + 2, idesc, 1u);
+          umma_f16(d, ad + 4, bd + 0, idesc, 1u);          // lo . hi
+          umma_f16(d, ad + 6, bd + 2, idesc, 1u);
+          umma_f16(d, ad + 0, bd + 4, idesc, 1u);          // hi . lo
+          umma_f16(d, ad + 2, bd + 6, idesc, 1u);
+        } else {
+          constexpr int KA = KP / 64;
+          const int ka = p >> 1;
+          const uint64_t ahi = ad + (uint64_t)(ka * 1024), alo = ad + (uint64_t)((KA + ka) * 1024);
+          if ((p & 1) == 0) {                              // piece holds g_hi: a_hi . g_hi and a_lo . g_hi
 #pragma unroll
-          for (int ks = 0; ks < CH_KP / 8; ++ks) {
-            const uint64_t dah = make_desc(ah + ks * 32, 16, 1024, 2), dal = make_desc(al + ks * 32, 16, 1024, 2);
-            const uint32_t boff = (uint32_t)(2 * ks * (2 * CH_KP / 32) * 512);
-            const uint64_t dbh = make_desc(bh + boff, 512, (2 * CH_KP / 32) * 512, 1), dbl = make_desc(bl + boff, 512, (2 * CH_KP / 32) * 512, 1);
-            umma_tf32(d, dah, dbh, idesc, ks > 0 ? 1u : 0u);
-            umma_tf32(d, dal, dbh, idesc, 1u);
-            umma_tf32(d, dah, dbl, idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_f16(d, ahi + 2 * ks, bd + 2 * ks, idesc, (p > 0 || ks > 0) ? 1u : 0u);
+              umma_f16(d, alo + 2 * ks, bd + 2 * ks, idesc, 1u);
+            }
+          } else {                                         // piece holds g_lo: a_hi . g_lo
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_f16(d, ahi + 2 * ks, bd + 2 * ks, idesc, 1u);
           }
-          umma_commit(&x_ready[k]);
-          itick(2);
         }
-        umma_commit(&node_empty[st]);
+      };
+      auto wait_a = [&](int k, int s) {
+        mbar_wait(&a_ready[k], (uint32_t)(s & 1));
+        tc_fence_after();
+        itick(1);
+      };
+      for (int s = 0; s < nsteps; ++s) {
+        const bool ev = itimer && s == nsteps / 2;
+        if (ev) g_chain_dbg[16] = (float)(clock64() - t_base);
+        if (C::TILE_MAJOR) {
+          // tile 0 waits for a piece, the last tile releases it
+#pragma unroll
+          for (int k = 0; k < TILES; ++k) {
+            wait_a(k, s);
+#pragma unroll
+            for (int p = 0; p < PIECES; ++p) {
+              const uint32_t q = (uint32_t)(s * PIECES + p), st = q % NSTAGE;
+              if (k == 0) { mbar_wait(&node_full[st], (q / NSTAGE) & 1u); itick(0); }
+              issue(k, p, st);
+              if (k == TILES - 1) umma_commit(&node_empty[st]);
+            }
+            umma_commit(&x_ready[k]);
+            itick(2);
+            if (ev && k < 4) g_chain_dbg[17 + k] = (float)(clock64() - t_base);      // issued tile k
+          }
+        } else {
+#pragma unroll
+          for (int p = 0; p < PIECES; ++p) {
+            const uint32_t q = (uint32_t)(s * PIECES + p), st = q % NSTAGE;
+            mbar_wait(&node_full[st], (q / NSTAGE) & 1u);
+            itick(0);
+#pragma unroll
+            for (int k = 0; k < TILES; ++k) {
+              if (p == 0) wait_a(k, s);
+              issue(k, p, st);
+              if (p == PIECES - 1) {
+                umma_commit(&x_ready[k]);
+                if (ev && k < 4) g_chain_dbg[17 + k] = (float)(clock64() - t_base);
+              }
+              itick(2);
+            }
+            umma_commit(&node_empty[st]);
+          }
+        }
       }
       if (itimer) for (int q = 0; q < 3; ++q) g_chain_dbg[4 + q] = (float)iacc[q];
     }
   } else {
-    // ===== epilogue warpgroup of tile k: one image row per thread =====
-    const int k = warp >> 2, quad = warp & 3;
+    // ===== epilogue: warpgroup g of tile k owns state columns [g*JW, (g+1)*JW) of every image row =====
+    const int wgi = warp >> 2, k = wgi / WG, g = wgi % WG, quad = warp & 3;
     const int row = quad * 32 + lane;
-    const int64_t t = ((int64_t)blockIdx.x * CH_TILES + k) * CH_TM + row;
+    const int64_t t = ((int64_t)blockIdx.x * TILES + k) * CH_TM + row;
     const bool live = t < a.B;
-    uint8_t* ah = a_base + k * 2 * CH_A_BYTES, *al = ah + CH_A_BYTES;
-    const uint32_t roff = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
-    const int r8 = row & 7;
-    float snew[CH_KP];
-    // start vector (mps.py:446-466)
+    uint8_t* at = a_base + k * C::A_BYTES;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(k * NCOL + g * JW);
+    int E = 0;               // true state = stored state * 2^E
+    int pos_prev = CH_TROW;  // exponent of the stored row maximum of the previous step
+    int sh_pred = CH_TROW - (CH_TROW + CH_TEXP);     // first guess: growth factor one (node maximum 2^TEXP)
+
+    // 8 scaled state values -> packed fp16 hi and lo
+    auto convert8 = [&](const float* v, float sc, uint4& hi, uint4& lo) {
+      __align__(16) __half2 h2[4];
+      __align__(16) __half2 l2[4];
 #pragma unroll
-    for (int j = 0; j < CH_KP; ++j)
-      snew[j] = a.start_kind == 0 ? ((j >= a.L && j < 2 * a.L) ? 1.f : 0.f) : (j < a.L ? 1.f : 0.f);
-    auto store_state = [&]() {
-#pragma unroll
-      for (int c = 0; c < CH_KP / 4; ++c) {
-        float4 hi, lo;
-        hi.x = tf32_round(snew[4 * c]); hi.y = tf32_round(snew[4 * c + 1]); hi.z = tf32_round(snew[4 * c + 2]); hi.w = tf32_round(snew[4 * c + 3]);
-        lo.x = snew[4 * c] - hi.x; lo.y = snew[4 * c + 1] - hi.y; lo.z = snew[4 * c + 2] - hi.z; lo.w = snew[4 * c + 3] - hi.w;
-        const uint32_t off = roff + (uint32_t)((c ^ r8) << 4);
-        *reinterpret_cast<float4*>(ah + off) = hi;
-        *reinterpret_cast<float4*>(al + off) = lo;
+      for (int q = 0; q < 4; ++q) {
+        const float x = v[2 * q] * sc, y = v[2 * q + 1] * sc;
+        h2[q] = __floats2half2_rn(x, y);
+        const float2 hf = __half22float2(h2[q]);
+        l2[q] = __floats2half2_rn(x - hf.x, y - hf.y);
       }
+      hi = *reinterpret_cast<const uint4*>(h2);
+      lo = *reinterpret_cast<const uint4*>(l2);
+    };
+    // 16-byte chunk kc (state columns 8 kc .. 8 kc + 7) of my A row
+    auto store8 = [&](int kc, const uint4& hi, const uint4& lo) {
+      uint32_t oh, ol;
+      if (KP == 32) { oh = k128_chunk_off(row, kc); ol = k128_chunk_off(row, 4 + kc); }
+      else {
+        constexpr int KA = KP / 64;
+        oh = (uint32_t)((kc >> 3) * 16384) + k128_chunk_off(row, kc & 7);
+        ol = (uint32_t)((KA + (kc >> 3)) * 16384) + k128_chunk_off(row, kc & 7);
+      }
+      *reinterpret_cast<uint4*>(at + oh) = hi;
+      *reinterpret_cast<uint4*>(at + ol) = lo;
+    };
+    // write 32 scaled state values (state columns j0 .. j0+31) as fp16 hi/lo chunks of my A row
+    auto store_chunk32 = [&](const float (&v)[32], int j0, float sc) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 hi, lo;
+        convert8(&v[8 * c], sc, hi, lo);
+        store8((j0 >> 3) + c, hi, lo);
+      }
+    };
+    auto publish = [&]() {
       fence_async_proxy();
       tc_fence_before();
       mbar_arrive(&a_ready[k]);
     };
-    if (nsteps > 0) store_state();
+    // start vector (mps.py:446-466): exactly representable, row maximum 1 -> shift by TROW
+    if (nsteps > 0) {
+#pragma unroll 1
+      for (int c = 0; c < JW / 32; ++c) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int jj = g * JW + c * 32 + j;
+          v[j] = a.start_kind == 0 ? ((jj >= a.L && jj < 2 * a.L) ? 1.f : 0.f) : (jj < a.L ? 1.f : 0.f);
+        }
+        store_chunk32(v, g * JW + c * 32, pow2f(CH_TROW));
+      }
+      E = -CH_TROW;
+      publish();
+    }
     const bool timer = blockIdx.x == 0 && tid == 0;
+    const bool evt = blockIdx.x == 0 && row == 0 && g == 0 && k < 2;      // event stamps of tiles 0 and 1
     long long tacc[4] = {0, 0, 0, 0}, tprev = timer ? clock64() : 0;
     auto tick = [&](int q) { if (timer) { long long now = clock64(); tacc[q] += now - tprev; tprev = now; } };
     // raw feature of a site for my image: pixel (in .x) or the precomputed phi; fetched TWO sites ahead so that the
-    // load latency never meets the sincos that consumes it
+    // load latency never meets the arithmetic that consumes it
     auto load_raw = [&](int step) -> float2 {
       if (!live || step >= nsteps) return make_float2(0.f, 0.f);
       const float* fs = a.feat + feat_site_offset(a.fm, a.B, a.first + step * a.dir);
@@ -240,62 +430,155 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_tc_kernel(ChainArgs a) {
       const float2 raw2 = load_raw(s + 2);          // in flight for two steps
       const float2 ph_next = phi_of_raw(raw1);      // loaded one step ago
       raw1 = raw2;
+      const int fs_exp = __ldg(a.exps + s);
+      const bool last = s + 1 == nsteps;
       tick(0);
       mbar_wait(&x_ready[k], (uint32_t)(s & 1));
       tc_fence_after();
+      if (evt && s == nsteps / 2) g_chain_dbg[32 + k * 8] = (float)(clock64() - t_base);        // x_ready seen
       tick(1);
-      float x0[32], x1[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(k * 2 * CH_KP);
-      tmem_ld32(taddr, x0);
-      tmem_ld32(taddr + CH_KP, x1);
+      // new state v[j] = phi_0 X[(0,j)] + phi_1 X[(1,j)], 32 of my columns at a time
+      auto chunk = [&](int c, float (&v)[32]) {
+        uint32_t x0[32], x1[32];
+        tmem_ld32_issue(taddr + c * 32, x0);
+        tmem_ld32_issue(taddr + KP + c * 32, x1);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < CH_KP; ++j) snew[j] = fmaf(ph.x, x0[j], ph.y * x1[j]);
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(ph.x, __uint_as_float(x0[j]), ph.y * __uint_as_float(x1[j]));
+      };
+      if (a.dbg == 1 && !last) {
+        publish();
+      } else if (last) {
+        // final environment in fp32: undo both exponents
+        const int e = E + fs_exp;
+#pragma unroll 1
+        for (int c = 0; c < JW / 32; ++c) {
+          float v[32];
+          chunk(c, v);
+          if (live) {
+            const int j0 = g * JW + c * 32;
+            float* o = a.out + t * a.Ds + j0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (j0 + j < a.Ds)
+                *reinterpret_cast<float4*>(o + j) = make_float4(scale_pow2(v[j], e), scale_pow2(v[j + 1], e), scale_pow2(v[j + 2], e), scale_pow2(v[j + 3], e));
+          }
+        }
+        tick(2);
+      } else {
+        // single pass with the predicted shift; redo (warp-uniformly: tcgen05.ld is warp-collective) if the realised
+        // row maximum leaves the safe window
+        int sh = max(-120, min(120, sh_pred));
+        float mx = 0.f;
+        {
+          const float sc = pow2f(sh);
+#pragma unroll 1
+          for (int c = 0; c < JW / 32; ++c) {
+            float v[32];
+            chunk(c, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fabsf(v[j]));
+            store_chunk32(v, g * JW + c * 32, sc);
+          }
+        }
+        if (WG > 1) {
+          // the row maximum spans the warpgroups of the tile: exchange the partial maxima (named barrier per tile)
+          mx_x[(k * WG + g) * CH_TM + row] = mx;
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "r"(WG * 128) : "memory");
+#pragma unroll
+          for (int o = 0; o < WG; ++o) mx = fmaxf(mx, mx_x[(k * WG + o) * CH_TM + row]);
+        }
+        const bool valid = mx > 0.f && mx < 3.0e38f;
+        const int ex = valid ? exponent_of(mx) : 0;
+        int pos = ex + sh;                       // exponent of the stored row maximum
+        tick(2);
+        if (__any_sync(0xffffffffu, valid && (pos > 14 || pos < CH_TROW - 10))) {
+          if (valid) sh = max(-120, min(120, CH_TROW - ex));
+          const float sc = pow2f(sh);
+#pragma unroll 1
+          for (int c = 0; c < JW / 32; ++c) {
+            float v[32];
+            chunk(c, v);
+            store_chunk32(v, g * JW + c * 32, sc);
+          }
+          pos = ex + sh;
+        }
+        if (WG > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "r"(WG * 128) : "memory");      // mx_x is reused next step
+        E += fs_exp - sh;
+        // next raw maximum ~ 2^pos * (growth seen now): growth = ex - pos_prev  (the node scale 2^13 is inside both)
+        if (valid) { sh_pred = CH_TROW - (pos + ex - pos_prev); pos_prev = pos; }
+        publish();
+        if (evt && s == nsteps / 2) g_chain_dbg[32 + k * 8 + 4] = (float)(clock64() - t_base);          // published
+      }
       ph = ph_next;
-      tick(2);
-      if (s + 1 < nsteps) store_state();
       tick(3);
     }
     if (timer) for (int q = 0; q < 4; ++q) g_chain_dbg[q] = (float)tacc[q];
-    if (live) {
+    if (nsteps == 0 && live && g == 0) {
       float* o = a.out + t * a.Ds;
-      for (int j = 0; j < a.Ds; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(snew[j], snew[j + 1], snew[j + 2], snew[j + 3]);
+      for (int j = 0; j < a.Ds; ++j) o[j] = a.start_kind == 0 ? ((j >= a.L && j < 2 * a.L) ? 1.f : 0.f) : (j < a.L ? 1.f : 0.f);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, TILES * NCOL);
+}
+
+template <int KP>
+int launch_chain_kp(const ChainArgs& a, const float* nodes, uint8_t* img, int32_t* exps, cudaStream_t st) {
+  if (a.nsteps > 0) {
+    chain_exp_kernel<<<a.nsteps, 1024, 0, st>>>(nodes, exps, a.Ds, a.first, a.dir);
+    TRMPS_LAUNCH_OK("chain_exp_kernel");
+    chain_prep_kernel<KP><<<296, 256, 0, st>>>(nodes, img, exps, a.Ds, a.first, a.dir, a.nsteps);
+    TRMPS_LAUNCH_OK("chain_prep_kernel");
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    TRMPS_CUDA_OK(cudaFuncSetAttribute(chain_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem<KP>()));
+    attr_set = true;
+  }
+  chain_tc_kernel<KP><<<(unsigned)ceil_div64(a.B, ChainCfg<KP>::TILES * CH_TM), chain_threads<KP>(), chain_smem<KP>(), st>>>(a);
+  TRMPS_LAUNCH_OK("chain_tc_kernel");
+  return TRMPS_OK;
+}
+
+int chain_kp(int Ds) { return Ds <= 32 ? 32 : Ds <= 64 ? 64 : 128; }
+int64_t chain_site_bytes(int Ds) {
+  const int kp = chain_kp(Ds);
+  return kp == 32 ? site_bytes<32>() : kp == 64 ? site_bytes<64>() : site_bytes<128>();
 }
 
 }  // namespace
 
-bool chain_tc_supported(int Ds) { return Ds <= CH_KP && Ds % 4 == 0; }
-int chain_tc_debug(float* out16) { return cudaMemcpyFromSymbol(out16, g_chain_dbg, 16 * sizeof(float)) == cudaSuccess ? 0 : -1; }
-int64_t chain_tc_image_floats(int nsteps) { return (int64_t)nsteps * 2 * CH_KP * 2 * CH_KP; }
+bool chain_tc_supported(int Ds) { return Ds <= 128 && Ds % 4 == 0; }
+int chain_tc_debug(float* out64) { return cudaMemcpyFromSymbol(out64, g_chain_dbg, 64 * sizeof(float)) == cudaSuccess ? 0 : -1; }
+// scratch for the images of `nsteps` sites plus their exponents (in floats)
+int64_t chain_tc_image_floats(int Ds, int nsteps) {
+  if (nsteps < 1) nsteps = 1;
+  return (int64_t)nsteps * (chain_site_bytes(Ds) / 4) + (((int64_t)nsteps + 3) / 4) * 4 + 8;
+}
 
 // runs `nsteps` chain steps starting at site `first` in direction dir from the boundary vector; writes the final
-// environment (B x Ds).  img: scratch of chain_tc_image_floats(nsteps) floats.
+// environment (B x Ds).  img: 16-byte aligned scratch of chain_tc_image_floats(Ds, nsteps) floats.
 int launch_chain_tc(const float* feat, int fm, int64_t B, int Ds, int L, const float* nodes, int first, int dir, int nsteps,
                     int start_kind, float* img, float* out, cudaStream_t st) {
   if (B <= 0) return TRMPS_OK;
   if (!chain_tc_supported(Ds)) {
-    set_error("chain_tc: Ds=%d not supported (<= %d)", Ds, CH_KP);
+    set_error("chain_tc: Ds=%d not supported (<= 128, multiple of 4)", Ds);
     return TRMPS_E_ARG;
-  }
-  if (nsteps > 0) {
-    chain_prep_kernel<<<296, 256, 0, st>>>(nodes, img, Ds, first, dir, nsteps);
-    TRMPS_LAUNCH_OK("chain_prep_kernel");
   }
   ChainArgs a;
   a.feat = feat; a.fm = fm; a.B = B; a.Ds = Ds; a.L = L; a.first = first; a.dir = dir; a.nsteps = nsteps;
-  a.start_kind = start_kind; a.img = img; a.out = out;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TRMPS_CUDA_OK(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM));
-    attr_set = true;
-  }
-  chain_tc_kernel<<<(unsigned)ceil_div64(B, CH_TILES * CH_TM), CH_THREADS, CH_SMEM, st>>>(a);
-  TRMPS_LAUNCH_OK("chain_tc_kernel");
-  return TRMPS_OK;
+  a.start_kind = start_kind; a.out = out;
+  static const int dbg_mode = getenv("TRMPS_CHAIN_DEBUG") ? atoi(getenv("TRMPS_CHAIN_DEBUG")) : 0;
+  a.dbg = dbg_mode;
+  uint8_t* image = reinterpret_cast<uint8_t*>(img);
+  int32_t* exps = reinterpret_cast<int32_t*>(image + (size_t)(nsteps < 1 ? 1 : nsteps) * chain_site_bytes(Ds));
+  a.img = image; a.exps = exps;
+  const int kp = chain_kp(Ds);
+  return kp == 32 ? launch_chain_kp<32>(a, nodes, image, exps, st)
+       : kp == 64 ? launch_chain_kp<64>(a, nodes, image, exps, st)
+                  : launch_chain_kp<128>(a, nodes, image, exps, st);
 }
 
 }  // namespace trmps

@@ -42,8 +42,20 @@ __host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { r
 __device__ __forceinline__ float2 phi_of_pixel(float x, int kind) {
   if (kind == TRMPS_FM_ONE_SQRT3) return make_float2(1.0f, 1.7320508075688772f * (2.0f * x - 1.0f));
   if (kind == TRMPS_FM_ONE_X) return make_float2(1.0f, x);
+  // TRMPS_FM_COS_SIN.  Pixels live in [0,1]: fold onto [0, pi/4] (1 - x is exact for x in [0.5,1]) and use the
+  // classic single-precision minimax kernels (~1 ulp there); anything else takes the library path.
   float s, c;
-  sincosf(1.5707963267948966f * x, &s, &c);   // TRMPS_FM_COS_SIN
+  if (x >= 0.f && x <= 1.f) {
+    const bool fold = x > 0.5f;
+    const float t = 1.5707963267948966f * (fold ? 1.f - x : x), z = t * t;
+    const float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f) * z, t, t);
+    const float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f) * z, z,
+                          fmaf(-0.5f, z, 1.f));
+    s = fold ? cp : sp;
+    c = fold ? sp : cp;
+  } else {
+    sincosf(1.5707963267948966f * x, &s, &c);
+  }
   return make_float2(c, s);
 }
 
@@ -154,8 +166,8 @@ int launch_grad_tc(const float* e_near, const float* e_far, const float* phi_nea
                    int64_t B, int Ds, int L, cudaStream_t st, float* dbg = nullptr);
 int grad_tc_splits(int64_t B, int Ds, int L, int sms);
 bool chain_tc_supported(int Ds);
-int chain_tc_debug(float* out16);
-int64_t chain_tc_image_floats(int nsteps);
+int chain_tc_debug(float* out64);
+int64_t chain_tc_image_floats(int Ds, int nsteps);
 int launch_chain_tc(const float* feat, int fm, int64_t B, int Ds, int L, const float* nodes, int first, int dir, int nsteps,
                     int start_kind, float* img, float* out, cudaStream_t st);
 int option_value(int option);

@@ -222,6 +222,26 @@ __global__ void special_to_matrix_kernel(const float* __restrict__ sp, float* __
   M[((int64_t)(m * Ds + i)) * ((int64_t)L * Ds) + (int64_t)l * Ds + k] = sp[idx];
 }
 
+// Inference as a bond with a unit far site: M[(m,i)][(l,n,k)] = special[l][m][i][k] for n = 0, zero for n = 1, and
+// phi_far = (1, 0) for every image.  This is the layout the tensor-core forward contraction consumes.
+__global__ void special_to_bond_kernel(const float* __restrict__ sp, float* __restrict__ M, float2* __restrict__ phi_far,
+                                       int Ds, int L, int64_t B) {
+  const int64_t total = (int64_t)L * 2 * Ds * Ds;
+  const int64_t Cc = (int64_t)2 * L * Ds;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % Ds);
+    int64_t r = idx / Ds;
+    const int i = (int)(r % Ds);
+    r /= Ds;
+    const int m = (int)(r % 2), l = (int)(r / 2);
+    float* row = M + (int64_t)(m * Ds + i) * Cc + (int64_t)(l * 2) * Ds;
+    row[k] = sp[idx];
+    row[Ds + k] = 0.f;
+  }
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < B; t += (int64_t)gridDim.x * blockDim.x)
+    phi_far[t] = make_float2(1.f, 0.f);
+}
+
 int launch_special_to_matrix(const float* special, float* M, int Ds, int L, cudaStream_t st) {
   int64_t total = (int64_t)L * 2 * Ds * Ds;
   special_to_matrix_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(special, M, Ds, L);
@@ -286,11 +306,14 @@ extern "C" int trmps_env_step(const float* feat_site, int32_t feature_map, int64
   return launch_env_step(feat_site, feature_map, B, Ds, dir, in_env, node_slot, din_dev, out_env, (cudaStream_t)stream);
 }
 
-extern "C" int trmps_debug_chain(float* out16) { return trmps::chain_tc_debug(out16); }
+extern "C" int trmps_debug_chain(float* out64) { return trmps::chain_tc_debug(out64); }
 
-extern "C" int64_t trmps_predict_work_floats(int64_t B, int32_t L, int32_t Ds) {
-  // 4 environment buffers, the special-node matrix, phi of the special site, one partial-logit buffer
-  return 4 * B * Ds + (int64_t)2 * Ds * L * Ds + 2 * B + B * L + 4096 /*alignment*/ + chain_tc_image_floats(1 << 14);
+extern "C" int64_t trmps_predict_work_floats(int64_t B, int32_t L, int32_t Ds, int32_t N) {
+  // 4 environment buffers, the special-node matrix, phi of the special site, one partial-logit buffer, and the
+  // fp16 node images of the longer of the two chains
+  return 4 * B * Ds + (int64_t)2 * Ds * L * Ds + 2 * B + B * L + 4096 /*alignment*/ +
+         (chain_tc_supported(Ds) ? chain_tc_image_floats(Ds, N) + 1024 : 0) +
+         (forward_tc_supported(Ds, L, 2) ? (int64_t)4 * L * Ds * Ds + forward_tc_image_floats(Ds, L) + 1024 : 0);
 }
 
 extern "C" int trmps_predict(const trmps_predict_desc* p, void* stream) {
@@ -313,14 +336,27 @@ extern "C" int trmps_predict(const trmps_predict_desc* p, void* stream) {
   float* fpart = phi_loc + 2 * B;
   const size_t slot = (size_t)2 * Ds * Ds;
   int rc;
-  if (option_value(2) == 0 && chain_tc_supported(Ds) && N <= (1 << 14)) {
+  if (option_value(2) == 0 && chain_tc_supported(Ds)) {
     // fused tensor-core chains: the environments never leave the SM between sites
     float* img = fpart + B * L;
-    img += (4 - ((uintptr_t)img / sizeof(float)) % 4) % 4;
+    img += (256 - ((uintptr_t)img / sizeof(float)) % 256) % 256;      // bulk copies want 16-byte alignment; keep 1 KB
     if ((rc = launch_chain_tc(p->feat, fm, B, Ds, L, p->nodes, 0, +1, p->loc, 0, img, buf[0], st))) return rc;
     if ((rc = launch_chain_tc(p->feat, fm, B, Ds, L, p->nodes, N - 1, -1, N - 1 - p->loc, 1, img, buf[2], st))) return rc;
-    if ((rc = launch_special_to_matrix(p->special, M, Ds, L, st))) return rc;
     if ((rc = trmps::launch_phi_site(p->feat + feat_site_offset(fm, B, p->loc), fm, B, phi_loc, st))) return rc;
+    if (option_value(1) == 0 && forward_tc_supported(Ds, L, 2)) {
+      // special-node contraction (mps.py:552-557) on the tensor cores: a bond whose far site is the identity
+      float* M2 = img + chain_tc_image_floats(Ds, N);
+      M2 += (256 - ((uintptr_t)M2 / sizeof(float)) % 256) % 256;
+      float* bimg = M2 + (int64_t)4 * L * Ds * Ds;
+      float* phi_far = buf[1];              // unused by the fused chains
+      special_to_bond_kernel<<<296, 256, 0, st>>>(p->special, M2, reinterpret_cast<float2*>(phi_far), Ds, L, B);
+      TRMPS_LAUNCH_OK("special_to_bond_kernel");
+      if ((rc = launch_forward_tc(buf[0], buf[2], phi_loc, phi_far, M2, bimg, fpart, B, Ds, L, p->dims + p->loc,
+                                  p->dims + p->loc + 1, st)))
+        return rc;
+      return launch_sum_round_logits(fpart, 1, B, L, p->round_output, p->logits, st);
+    }
+    if ((rc = launch_special_to_matrix(p->special, M, Ds, L, st))) return rc;
     if ((rc = launch_forward(buf[0], buf[2], phi_loc, nullptr, M, fpart, 1, B, Ds, L, 1, p->dims + p->loc, st))) return rc;
     return launch_sum_round_logits(fpart, 1, B, L, p->round_output, p->logits, st);
   }

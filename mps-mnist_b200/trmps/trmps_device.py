@@ -106,7 +106,7 @@ def predict(weights, feature, feature_map, round_output=False, out=None):
     N, L, Ds = weights.N, weights.L, weights.Ds
     B = feature.shape[1]
     dev = weights.device
-    work = torch.empty(int(lib.trmps_predict_work_floats(B, L, Ds)), dtype=torch.float32, device=dev)
+    work = torch.empty(int(lib.trmps_predict_work_floats(B, L, Ds, N)), dtype=torch.float32, device=dev)
     logits = out if out is not None else torch.empty((B, L), dtype=torch.float32, device=dev)
     p = nat.PredictDesc(N=N, d=2, L=L, Ds=Ds, B=B, loc=weights.loc, feature_map=feature_map,
                         round_output=int(bool(round_output)), reserved=0,

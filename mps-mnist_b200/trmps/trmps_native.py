@@ -62,7 +62,7 @@ _SIGNATURES = {
     "trmps_profile_begin": (C.c_int, [C.c_int32]),
     "trmps_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]),
     "trmps_sweep_layout": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Layout)]),
-    "trmps_predict_work_floats": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "trmps_predict_work_floats": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "trmps_feature_map": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "trmps_env_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),

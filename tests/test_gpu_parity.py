@@ -413,7 +413,9 @@ def test_tcgen05_forward_matches_simt_and_fp64(D, B, direction):
     assert np.array_equal(results[nat.FWD_TCGEN05].argmax(1), f64.argmax(1)) or rel(results[nat.FWD_TCGEN05], f64) < 1e-6
 
 
-@pytest.mark.parametrize("N,B,D,loc", [(16, 333, None, None), (40, 1500, 32, 13), (24, 700, 32, 0), (24, 700, 24, 23)])
+@pytest.mark.parametrize("N,B,D,loc", [(16, 333, None, None), (40, 1500, 32, 13), (24, 700, 32, 0), (24, 700, 24, 23),
+                                       (30, 900, 48, 11), (20, 600, 64, 19), (26, 520, 100, 9), (22, 300, 120, 0),
+                                       (18, 257, 128, 17)])
 def test_fused_tcgen05_chain_matches_simt_and_fp64(N, B, D, loc):
     L = 10
     pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=81, fm=o.FM_COS_SIN, full_bond=D, loc=loc)

@@ -28,7 +28,12 @@ flops = B * ((N - 1) * 2.0 * 2 * D * D + 2.0 * L * 2 * D * D)
 print("predict N=%d D=%d B=%d: %.2f ms  -> %.2f M images/s, %.1f TFLOP/s algorithmic, pixel stream %.0f GB/s; logits mean %.4f" %
       (N, D, B, ms, B / ms / 1e3, flops / ms / 1e9, 4.0 * N * B / ms / 1e6, float(out.mean())))
 import ctypes as C
-buf = (C.c_float * 16)()
+buf = (C.c_float * 64)()
 nat.load().trmps_debug_chain(buf)
 print("chain epilogue (CTA0 tile0) cycles: other/pixel %.0f  wait x_ready %.0f  tmem ld + combine %.0f  store_state+arrive %.0f  (last launch, %d steps)" % (buf[0], buf[1], buf[2], buf[3], N - 1 - loc))
 print("chain issuer cycles: wait node %.0f  wait a_ready %.0f  issue+commit %.0f" % (buf[4], buf[5], buf[6]))
+t0 = buf[16]
+print("events of the middle step (cycles after the issuer entered the step):")
+print("  issuer: issued (tile,half) " + "  ".join("T%dh%d %+.0f" % (i % 2, i // 2, buf[17 + i] - t0) for i in range(4)))
+for k in range(2):
+    print("  tile %d epilogue: x_ready h0 %+.0f  h0 converted %+.0f  x_ready h1 %+.0f  published %+.0f" % (k, buf[32 + 8 * k] - t0, buf[32 + 8 * k + 3] - t0, buf[32 + 8 * k + 1] - t0, buf[32 + 8 * k + 4] - t0))
