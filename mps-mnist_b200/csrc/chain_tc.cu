@@ -438,13 +438,15 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
       if (evt && s == nsteps / 2) g_chain_dbg[32 + k * 8] = (float)(clock64() - t_base);        // x_ready seen
       tick(1);
       // new state v[j] = phi_0 X[(0,j)] + phi_1 X[(1,j)], 32 of my columns at a time
-      auto chunk = [&](int c, float (&v)[32]) {
+      // (sc is a power of two, so folding it into phi is exact)
+      auto chunk = [&](int c, float (&v)[32], float sc = 1.f) {
         uint32_t x0[32], x1[32];
         tmem_ld32_issue(taddr + c * 32, x0);
         tmem_ld32_issue(taddr + KP + c * 32, x1);
         tmem_ld_wait();
+        const float p0 = ph.x * sc, p1 = ph.y * sc;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(ph.x, __uint_as_float(x0[j]), ph.y * __uint_as_float(x1[j]));
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(p0, __uint_as_float(x0[j]), p1 * __uint_as_float(x1[j]));
       };
       if (a.dbg == 1 && !last) {
         publish();
@@ -475,10 +477,10 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
 #pragma unroll 1
           for (int c = 0; c < JW / 32; ++c) {
             float v[32];
-            chunk(c, v);
+            chunk(c, v, sc);                   // already scaled
 #pragma unroll
             for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fabsf(v[j]));
-            store_chunk32(v, g * JW + c * 32, sc);
+            store_chunk32(v, g * JW + c * 32, 1.f);
           }
         }
         if (WG > 1) {
@@ -489,8 +491,8 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
           for (int o = 0; o < WG; ++o) mx = fmaxf(mx, mx_x[(k * WG + o) * CH_TM + row]);
         }
         const bool valid = mx > 0.f && mx < 3.0e38f;
-        const int ex = valid ? exponent_of(mx) : 0;
-        int pos = ex + sh;                       // exponent of the stored row maximum
+        int pos = valid ? exponent_of(mx) : 0;   // exponent of the stored row maximum
+        const int ex = pos - sh;                 // exponent of the raw maximum
         tick(2);
         if (__any_sync(0xffffffffu, valid && (pos > 14 || pos < CH_TROW - 10))) {
           if (valid) sh = max(-120, min(120, CH_TROW - ex));

@@ -19,7 +19,12 @@ __device__ inline uint32_t off_k_sw128_h(int r, int k) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 3) ^ (r & 7)) & 7) << 4) + (k & 7) * 2);
 }
 
-struct Params { int N; int reps; int kind; int nacc; };   // kind 0 = f16, 1 = tf32 (timing only)
+// K-major SW64, 2-byte elements: rows of 64 B (32 halfs), 8 rows per 512 B atom, 16 B chunks XORed with (row>>1)&3
+__device__ inline uint32_t off_k_sw64_h(int r, int k) {
+  return (uint32_t)((r >> 3) * 512 + (r & 7) * 64 + ((((k >> 3) ^ (r >> 1)) & 3) << 4) + (k & 7) * 2);
+}
+
+struct Params { int N; int reps; int kind; int nacc; int b64; };   // b64: B operand in K-major SWIZZLE_64B (64-byte rows, K = 32)   // kind 0 = f16, 1 = tf32 (timing only)
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(Params p, float* out, long long* cyc) {
   extern __shared__ uint8_t raw[];
@@ -32,7 +37,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p, float* out, lon
   for (int i = tid; i < 49152 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 0.f;
   __syncthreads();
   for (int e = tid; e < 128 * 64; e += 128) { int m = e / 64, k = e % 64; *reinterpret_cast<__half*>(sa + off_k_sw128_h(m, k)) = __float2half(aval(m, k)); }
-  for (int e = tid; e < p.N * 64; e += 128) { int n = e / 64, k = e % 64; *reinterpret_cast<__half*>(sb + off_k_sw128_h(n, k)) = __float2half(bval(n, k)); }
+  if (p.b64) { for (int e = tid; e < p.N * 32; e += 128) { int n = e / 32, k = e % 32; *reinterpret_cast<__half*>(sb + off_k_sw64_h(n, k)) = __float2half(bval(n, k)); } }
+  else for (int e = tid; e < p.N * 64; e += 128) { int n = e / 64, k = e % 64; *reinterpret_cast<__half*>(sb + off_k_sw128_h(n, k)) = __float2half(bval(n, k)); }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -56,20 +62,29 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p, float* out, lon
     d |= (uint64_t)2 << 61;
     return d;
   };
+  auto mk64 = [&](uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((512u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+  };
   long long t0 = 0;
   if (tid == 0) {
     const uint32_t idesc_h = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t idesc_t = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     if (p.reps == 1) {     // correctness pass: 4 MMAs, first one overwrites
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t xa = mk(smem_u32(sa) + ks * 32), xb = mk(smem_u32(sb) + ks * 32);
+      for (int ks = 0; ks < (p.b64 ? 2 : 4); ++ks) {
+        const uint64_t xa = mk(smem_u32(sa) + ks * 32), xb = p.b64 ? mk64(smem_u32(sb) + ks * 32) : mk(smem_u32(sb) + ks * 32);
         asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n\t}"
                      ::"r"(tbase), "l"(xa), "l"(xb), "r"(idesc_h), "r"(ks > 0 ? 1u : 0u) : "memory");
       }
     }
     uint64_t da[4], db[4];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) { da[ks] = mk(smem_u32(sa) + ks * 32); db[ks] = mk(smem_u32(sb) + ks * 32); }
+    for (int ks = 0; ks < 4; ++ks) { da[ks] = mk(smem_u32(sa) + ks * 32); db[ks] = p.b64 ? mk64(smem_u32(sb) + (ks & 1) * 32 + (ks >> 1) * 16384) : mk(smem_u32(sb) + ks * 32); }
     const uint32_t idesc = p.kind == 0 ? idesc_h : idesc_t;
     const uint32_t amask = (uint32_t)(p.nacc - 1), nn = (uint32_t)p.N;
     t0 = clock64();
@@ -116,12 +131,12 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p, float* out, lon
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512u) : "memory");
 }
 
-int run(int N, int reps, int kind, bool check, int nacc = 1) {
+int run(int N, int reps, int kind, bool check, int nacc = 1, int b64 = 0) {
   float* out; long long* cyc;
   cudaMalloc(&out, 128 * 256 * 4); cudaMalloc(&cyc, 64);
   cudaMemset(out, 0xff, 128 * 256 * 4); cudaMemset(cyc, 0, 64);
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 51200 + 1024);
-  Params p{N, reps, kind, nacc};
+  Params p{N, reps, kind, nacc, b64};
   probe_kernel<<<1, 128, 51200 + 1024>>>(p, out, cyc);
   cudaError_t e = cudaDeviceSynchronize();
   static float h[128 * 256]; long long hc[8];
@@ -129,16 +144,16 @@ int run(int N, int reps, int kind, bool check, int nacc = 1) {
   if (check) {
     int bad = 0; double maxerr = 0;
     for (int m = 0; m < 128; ++m) for (int n = 0; n < N; ++n) {
-      double want = 0; for (int k = 0; k < 64; ++k) want += (double)aval(m, k) * bval(n, k);
+      double want = 0; for (int k = 0; k < (b64 ? 32 : 64); ++k) want += (double)aval(m, k) * bval(n, k);
       double err = fabs((double)h[m * 256 + n] - want);
       if (!(err < 1e-3)) ++bad;
       if (err > maxerr) maxerr = err;
     }
-    printf("f16 K-major SW128  N=%3d: err=%s bad=%d/%d maxabs=%.3g  D[0][0..2]=%g %g %g\n", N, cudaGetErrorString(e), bad, 128 * N, maxerr, h[0], h[1], h[2]);
+    printf("f16 K-major %s  N=%3d: err=%s bad=%d/%d maxabs=%.3g  D[0][0..2]=%g %g %g\n", b64 ? "A SW128 / B SW64" : "SW128", N, cudaGetErrorString(e), bad, 128 * N, maxerr, h[0], h[1], h[2]);
   } else {
     const int nm = reps * 4;
     const double macs = (double)nm * 128 * N * (kind == 0 ? 16 : 8);
-    printf("%s nacc=%d N=%3d: %d MMAs in %lld cycles -> %.1f cycles/MMA, %.0f MAC/clk/SM  (%s)\n", kind == 0 ? "f16 " : "tf32", nacc, N, nm, hc[0],
+    printf("%s%s nacc=%d N=%3d: %d MMAs in %lld cycles -> %.1f cycles/MMA, %.0f MAC/clk/SM  (%s)\n", kind == 0 ? "f16 " : "tf32", b64 ? " (B SW64)" : "", nacc, N, nm, hc[0],
            (double)hc[0] / nm, macs / (double)hc[0], cudaGetErrorString(e));
   }
   cudaFree(out); cudaFree(cyc);
@@ -147,8 +162,10 @@ int run(int N, int reps, int kind, bool check, int nacc = 1) {
 
 int main() {
   for (int N : {64, 128, 256}) if (run(N, 1, 0, true)) return 1;
+  for (int N : {128, 256}) if (run(N, 1, 0, true, 1, 1)) return 1;
   for (int kind : {0, 1}) for (int N : {64, 128, 256}) if (run(N, 256, kind, false)) return 1;
   for (int kind : {0, 1}) for (int N : {64, 128}) for (int na : {2, 4}) if (run(N, 256, kind, false, na)) return 1;
   for (int kind : {0, 1}) if (run(256, 256, kind, false, 2)) return 1;
+  for (int N : {128, 256}) if (run(N, 256, 0, false, 1, 1)) return 1;
   return 0;
 }
