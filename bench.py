@@ -153,6 +153,21 @@ def cpu_sweep_rate(B_s, bonds, D, L, seed=0, reps=1):
     return B_s * bonds / best, best, os.cpu_count()
 
 
+def cpu_inference_rate(B_s, N, D, L, seed=0):
+    """Times the oracle's MPS.predict (mps.py:521-560 restated: one batched chain step per site) on the host cores
+    for a B_s-image sample at the cfg3 shape.  Returns (images/s, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import trmps_oracle as o
+    pix, _ = synthetic_pixels(N, B_s, L, seed)
+    phi = o.feature_map(pix, o.FM_COS_SIN)
+    nodes = full_bond_mps(N, 2, L, D, N // 2)
+    o.predict(nodes, N // 2, phi[:, :64], L)
+    t0 = time.perf_counter()
+    o.predict(nodes, N // 2, phi, L)
+    dt = time.perf_counter() - t0
+    return B_s / dt, dt
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -278,12 +293,9 @@ def run_ours(args, rank, local_rank, world):
     h2d = pix.nbytes + lab.nbytes + sum(w.nbytes for w in nodes)
     d2h = sum(w.nbytes for w in out_nodes) + 4
 
-    # second headline metric: inference images/s at cfg5 (N=784, D=32, 1M images per GPU, raw pixels in HBM)
-    inference = None
-    if not args.no_inference:
-        del optim, st
-        torch.cuda.empty_cache()
-        Ni, Di, Bi = 784, 32, args.inference_images
+    # second headline metric: inference images/s (MPS.predict on raw pixels resident in HBM, fused cos/sin map):
+    # at the headline shape cfg3 (N=196, D=120) and at cfg5 (N=784, D=32, 1M images per GPU)
+    def inference_rate(Ni, Di, Bi, label):
         inodes = full_bond_mps(Ni, 2, L, Di, Ni // 2)
         w = dev.DeviceWeights(inodes, Ni // 2, L, dev.bond_stride(inodes, Ni // 2, L), device)
         gen = torch.Generator(device=device).manual_seed(7 + rank)
@@ -293,21 +305,30 @@ def run_ours(args, rank, local_rank, world):
             dev.predict(w, ipix, nat.FM_COS_SIN, out=iout)
         barrier()
         i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
         i0.record()
-        for _ in range(3):
+        for _ in range(reps):
             dev.predict(w, ipix, nat.FM_COS_SIN, out=iout)
         i1.record()
         barrier()
-        ims = torch.tensor([i0.elapsed_time(i1) / 3.0], device=device)
+        ims = torch.tensor([i0.elapsed_time(i1) / reps], device=device)
         if world > 1:
             dist.all_reduce(ims, op=dist.ReduceOp.MAX)
         ims = float(ims.item())
         iflops = Bi * ((Ni - 1) * 2.0 * 2 * Di * Di + 2.0 * L * 2 * Di * Di)
-        inference = dict(metric="inference_images_per_sec", value=world * Bi / (ims * 1e-3), unit="images/s", ms_per_pass=ims,
-                         config="cfg5: N=784 D=32 L=10, %d images per GPU, raw pixels resident in HBM, fused cos/sin map" % Bi,
-                         algorithmic_tflops=iflops / (ims * 1e-3) / 1e12,
-                         pixel_stream_gbs=4.0 * Ni * Bi / (ims * 1e-3) / 1e9)
-        del ipix, iout, w
+        return dict(metric="inference_images_per_sec", value=world * Bi / (ims * 1e-3), unit="images/s", ms_per_pass=ims,
+                    config="%s: N=%d D=%d L=10, %d images per GPU, raw pixels resident in HBM, fused cos/sin map, "
+                           "fp16 hi/lo split chain on tcgen05 (FP32-equivalent accuracy)" % (label, Ni, Di, Bi),
+                    algorithmic_tflops=world * iflops / (ims * 1e-3) / 1e12,
+                    pixel_stream_gbs=world * 4.0 * Ni * Bi / (ims * 1e-3) / 1e9)
+
+    inference = inference_cfg5 = None
+    if not args.no_inference:
+        del optim, st
+        torch.cuda.empty_cache()
+        inference = inference_rate(N, D, args.inference_images_cfg3, "cfg3")
+        torch.cuda.empty_cache()
+        inference_cfg5 = inference_rate(784, 32, args.inference_images, "cfg5")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -337,12 +358,16 @@ def run_ours(args, rank, local_rank, world):
                              bound="tensor", achieved=achieved, peak=tf32_peak, unit="TFLOP/s",
                              frac=achieved / tf32_peak, traffic=None, peak_source="%s bf16 sustained / 2 (TF32)" % peaks["source"],
                              avg_launch_ms=fwd_ms / max(fwd_n, 1), launches=fwd_n),
-               breakdown_ms_per_step=breakdown, inference=inference)
+               breakdown_ms_per_step=breakdown, inference=inference, inference_cfg5=inference_cfg5)
     if world == 1 and not args.no_cpu_baseline:
         r, dt, cores = cpu_sweep_rate(args.cpu_sample_images, args.cpu_sample_bonds, D, L)
         out["cpu_baseline"] = dict(value=r, unit=UNIT, cores=cores, kind="port",
                                    sample="%d images x %d full-size bond updates (%.1f s), literal reference graph in NumPy"
                                           % (args.cpu_sample_images, args.cpu_sample_bonds, dt))
+        if not args.no_inference:
+            ri, dti = cpu_inference_rate(4000, N, D, L)
+            out["cpu_baseline"].update(inference_value=ri, inference_unit="images/s",
+                                       inference_sample="cfg3 predict on 4000 images (%.1f s), NumPy chain" % dti)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -358,14 +383,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images-per-gpu", type=int, default=CFG["B"])
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample-images", type=int, default=2000)
-    ap.add_argument("--cpu-sample-bonds", type=int, default=3)
+    ap.add_argument("--cpu-sample-images", type=int, default=6000)
+    ap.add_argument("--cpu-sample-bonds", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --images-per-gpu images on every GPU (default); strong: that many images in total, sharded")
     ap.add_argument("--lr", type=float, default=1e-4, help="rate_of_change of the sweep (MPSTrainingParameters)")
-    ap.add_argument("--inference-images", type=int, default=1000000)
+    ap.add_argument("--inference-images", type=int, default=1000000, help="cfg5 images per GPU")
+    ap.add_argument("--inference-images-cfg3", type=int, default=120000, help="cfg3 (N=196, D=120) inference images per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

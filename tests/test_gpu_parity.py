@@ -433,3 +433,29 @@ def test_fused_tcgen05_chain_matches_simt_and_fp64(N, B, D, loc):
     margin = np.sort(want, axis=1)
     clear = (margin[:, -1] - margin[:, -2]) > 1e-4 * np.abs(margin[:, -1])
     assert np.array_equal(res[nat.CHAIN_TCGEN05].argmax(1)[clear], want.argmax(1)[clear])
+
+
+@pytest.mark.parametrize("D", [24, 56, 120])
+def test_fused_chain_tracks_exponents_over_wild_scales(D):
+    """The fp16 chain carries one power-of-two exponent per image row and per node; sites whose scale jumps by many
+    orders of magnitude defeat the growth prediction and take the redo path.  Result must still be FP32-accurate."""
+    N, B, L, loc = 28, 400, 10, 13
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=91, fm=o.FM_COS_SIN, full_bond=D, loc=loc)
+    rng = np.random.default_rng(3)
+    scales = 10.0 ** rng.integers(-6, 7, size=N)
+    scales[loc] = 1.0
+    scales[-1] = 1.0 / np.prod(scales[:-1])              # keep the logits in range
+    nodes = [(n * np.float32(sc)).astype(np.float32) for n, sc in zip(nodes, scales)]
+    w = dev.DeviceWeights(nodes, loc, L, dev.bond_stride(nodes, loc, L), cuda())
+    got = dev.predict(w, torch.from_numpy(pix).cuda(), nat.FM_COS_SIN).cpu().numpy()
+    try:
+        nat.set_option(nat.OPT_CHAIN_IMPL, nat.CHAIN_SIMT)
+        simt = dev.predict(w, torch.from_numpy(pix).cuda(), nat.FM_COS_SIN).cpu().numpy()
+    finally:
+        nat.set_option(nat.OPT_CHAIN_IMPL, nat.CHAIN_TCGEN05)
+    want = o.predict([n.astype(np.float64) for n in nodes], loc, phi.astype(np.float64), L)
+    assert np.isfinite(got).all()
+    print("wild scales D=%d: fp16-split chain %.2e, fp32 SIMT chain %.2e (relative to fp64)" % (D, rel(got, want), rel(simt, want)))
+    # hi + lo fp16 carries 22 mantissa bits (as 3xTF32 does): a few times the FP32 rounding error, well inside 1e-4
+    assert rel(got, want) < 5e-5
+    assert rel(simt, want) < 1e-5

@@ -21,4 +21,9 @@ for L in [int(v) for v in (sys.argv[2:] or ["1", "10"])]:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); st.bond_split(loc, +1, opt); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
+    ns = int(st.iwork.cpu()[nat.I_SVD_SWEEPS]); R = 2 * D
+    nbk = (R + 7) // 8; rounds = (nbk + (nbk & 1) - 1) * ns
+    dbg = st.work[st.layout.red: st.layout.red + 8].cpu().numpy()
+    print("   per round (CTA 0, cycles): load %.0f  gram %.0f  rotate %.0f  replay %.0f  store+publish %.0f  grid sync/sweep %.0f  flag wait %.0f   (%d rounds, total %.0f cycles)" %
+          (dbg[0] / rounds, dbg[1] / rounds, dbg[2] / rounds, dbg[3] / rounds, dbg[4] / rounds, dbg[5] / ns, dbg[6] / rounds, rounds, dbg[:7].sum()))
     print("L=%d D=%d bond %s: split %.3f ms (min of %s), sweeps %d" % (L, D, tuple(bm.shape), min(ts), ["%.3f" % t for t in ts], int(st.iwork.cpu()[nat.I_SVD_SWEEPS])))
