@@ -253,6 +253,7 @@ def run_ours(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    sweeps0 = int(st.iwork[nat.I_N_SWEEPS].item())
     nat.profile_begin(200000)
     l0 = nat.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -341,6 +342,29 @@ def run_ours(args, rank, local_rank, world):
     fwd_flops_total = (fwd_n - 2 * args.steps) * flops_per_launch + 2 * args.steps * 2.0 * B * L * 4 * (2 * L) * D
     achieved = fwd_flops_total / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else 0.0
     breakdown = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
+    roofline_fwd = dict(kernel="forward_tc_kernel, tcgen05 3xTF32 (f(bond) and f(delta): 2 of the 3 dense contractions per update; "
+                               "achieved counts algorithmic FP32 flops, the tensor pipe executes 3x as many TF32 flops)",
+                        bound="tensor", achieved=achieved, peak=tf32_peak, unit="TFLOP/s", frac=achieved / tf32_peak, traffic=None,
+                        peak_source="%s bf16 sustained / 2 (TF32)" % peaks["source"], avg_launch_ms=fwd_ms / max(fwd_n, 1),
+                        launches=fwd_n, share_of_step=fwd_ms / ms_total)
+    # dominant kernel of the step: the one-sided Jacobi split.  Its streaming requirement is the row exchange: every
+    # round each of the R/16 row-block pairs is loaded and stored once (R x (Cc + R) floats each way per round,
+    # R/8 - 1 rounds per sweep); the working set (2.9 MB) lives in L2, so this is L2 traffic, not DRAM.
+    Dp = dev.bond_stride(nodes, loc, L, D)
+    R_, Cc_ = 2 * Dp, 2 * L * Dp
+    svd_ms, svd_n = prof["svd"]
+    total_sweeps = int(iw[nat.I_N_SWEEPS]) - sweeps0
+    rounds_per_sweep = (2 * D + 7) // 8 - 1
+    svd_bytes = total_sweeps * rounds_per_sweep * 2.0 * (2 * D) * (Cc_ + R_) * 4
+    svd_gbs = svd_bytes / (svd_ms * 1e-3) / 1e9 if svd_ms > 0 else 0.0
+    roofline_svd = dict(kernel="svd_jacobi_cluster_kernel (+ norms/finalize/scatter): one-sided block Jacobi, %d splits, %.1f sweeps "
+                               "per split; bound by the %d dependent rounds per sweep (flag hand-off, cluster Gram reduction, "
+                               "rotation recurrences: ~21k cycles per round), not by bandwidth or flops" %
+                               (svd_n, total_sweeps / max(1.0, float(svd_n)), rounds_per_sweep),
+                        bound="hbm", achieved=svd_gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=svd_gbs / peaks["hbm_gbs"],
+                        traffic=None, peak_source="%s HBM copy bandwidth" % peaks["source"],
+                        avg_launch_ms=svd_ms / max(1.0, float(svd_n)), share_of_step=svd_ms / ms_total,
+                        note="algorithmic bytes = row-exchange traffic through L2; DRAM traffic is the 2.9 MB bond once")
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                ms_per_step=ms_total / args.steps, higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32",
                data="synthetic",
@@ -353,11 +377,7 @@ def run_ours(args, rank, local_rank, world):
                clocks=clocks, gpu_launches=int(launches),
                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                         steps=args.e2e_steps, last_cost=last_cost),
-               roofline=dict(kernel="forward_tc_kernel, tcgen05 3xTF32 (f(bond) and f(delta): 2 of the 3 dense contractions per update; "
-                                    "achieved counts algorithmic FP32 flops, the tensor pipe executes 3x as many TF32 flops)",
-                             bound="tensor", achieved=achieved, peak=tf32_peak, unit="TFLOP/s",
-                             frac=achieved / tf32_peak, traffic=None, peak_source="%s bf16 sustained / 2 (TF32)" % peaks["source"],
-                             avg_launch_ms=fwd_ms / max(fwd_n, 1), launches=fwd_n),
+               roofline=roofline_svd, roofline_forward=roofline_fwd,
                breakdown_ms_per_step=breakdown, inference=inference, inference_cfg5=inference_cfg5)
     if world == 1 and not args.no_cpu_baseline:
         r, dt, cores = cpu_sweep_rate(args.cpu_sample_images, args.cpu_sample_bonds, D, L)

@@ -75,6 +75,7 @@ enum {
   TRMPS_I_N_REVERT = 4,   /* running count: updates rejected because cost did not drop */
   TRMPS_I_N_EXHAUST = 5,  /* running count: Armijo loops that ran out of trials */
   TRMPS_I_N_UPDATES = 6,  /* running count: bond updates performed */
+  TRMPS_I_N_SWEEPS = 7,   /* running count: Jacobi sweeps over all splits */
   TRMPS_I_SVD_ROT = 8,    /* [8 .. 8+64): per-sweep rotation counters of the running SVD */
   TRMPS_I_BARRIER = 80,   /* [80 .. 84): grid-barrier words of the SVD kernel */
   TRMPS_I_COUNT = 96

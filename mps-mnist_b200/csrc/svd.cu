@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(SVD_THREADS) svd_jacobi_kernel(SvdArgs a) {
   }
   if (blockIdx.x == 0 && tid == 0) {
     a.iscal[TRMPS_I_SVD_SWEEPS] = sweeps_used;
+    a.iscal[TRMPS_I_N_SWEEPS] += sweeps_used;
     if (a.dbg) for (int k = 0; k < 6; ++k) a.dbg[k] = (float)tacc[k];
   }
 }
@@ -625,6 +626,7 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
   }
   if (blockIdx.x == 0 && tid == 0) {
     a.iscal[TRMPS_I_SVD_SWEEPS] = sweeps_used;
+    a.iscal[TRMPS_I_N_SWEEPS] += sweeps_used;
     if (a.dbg) for (int k = 0; k < 8; ++k) a.dbg[k] = (float)tacc[k];
   }
 }
