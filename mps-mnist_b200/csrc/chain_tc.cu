@@ -82,7 +82,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) { } }
+// blocking wait; the suspend-time hint lets the waiting warp sleep in hardware (it is woken when the phase completes)
+// instead of spinning through issue slots that the epilogue warps need
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -212,7 +223,8 @@ struct ChainArgs {
   int dbg;       // development: 1 = epilogue skips TMEM reads and A-tile stores, 2 = loader skips the copies (rate experiments; results invalid)
 };
 
-template <int KP>
+// DBG compiles in the clock64 phase timers / event stamps and the rate-experiment switches (TRMPS_CHAIN_DEBUG)
+template <int KP, bool DBG>
 __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainArgs a) {
   using C = ChainCfg<KP>;
   constexpr int TILES = C::TILES, WG = C::WG, NSTAGE = C::NSTAGE, PIECES = C::PIECES, NCOL = 2 * KP, JW = KP / WG;
@@ -233,7 +245,7 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
   const int nsteps = a.nsteps;
 
   if (tid == 0) {
-    t_base = clock64();
+    if (DBG) t_base = clock64();
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&node_full[s], 1); mbar_init(&node_empty[s], 1); }
     for (int k = 0; k < TILES; ++k) { mbar_init(&a_ready[k], WG * 128); mbar_init(&x_ready[k], 1); }
     fence_barrier_init();
@@ -252,7 +264,7 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
       for (int p = 0; p < npieces; ++p) {
         const int st = p % NSTAGE;
         if (p >= NSTAGE) mbar_wait(&node_empty[st], (uint32_t)(((p / NSTAGE) - 1) & 1));
-        if (a.dbg == 2) { mbar_arrive(&node_full[st]); continue; }      // experiment: no node traffic (results invalid)
+        if (DBG && a.dbg == 2) { mbar_arrive(&node_full[st]); continue; }      // experiment: no node traffic (results invalid)
         mbar_expect_tx(&node_full[st], C::PIECE_BYTES);
         bulk_g2s(n_base + st * C::PIECE_BYTES, a.img + (size_t)p * C::PIECE_BYTES, C::PIECE_BYTES, &node_full[st]);
       }
@@ -263,7 +275,7 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
       // kind::f16: fp16 x fp16 -> fp32, both operands K-major, N = 2*KP, M = 128
       const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(CH_TM >> 4) << 24);
       const uint64_t adesc0 = make_desc_k128(smem_u32(a_base)), bdesc0 = make_desc_k128(smem_u32(n_base));
-      const bool itimer = blockIdx.x == 0;
+      const bool itimer = DBG && blockIdx.x == 0;
       long long iacc[3] = {0, 0, 0}, iprev = clock64();
       auto itick = [&](int q) { if (itimer) { long long now = clock64(); iacc[q] += now - iprev; iprev = now; } };
       // MMAs of (tile k, piece p of the site).  descriptor start addresses count 16-byte units: +2 per K=16 step
@@ -408,17 +420,25 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
       E = -CH_TROW;
       publish();
     }
-    const bool timer = blockIdx.x == 0 && tid == 0;
-    const bool evt = blockIdx.x == 0 && row == 0 && g == 0 && k < 2;      // event stamps of tiles 0 and 1
+    const bool timer = DBG && blockIdx.x == 0 && tid == 0;
+    const bool evt = DBG && blockIdx.x == 0 && row == 0 && g == 0 && k < 2;      // event stamps of tiles 0 and 1
     long long tacc[4] = {0, 0, 0, 0}, tprev = timer ? clock64() : 0;
     auto tick = [&](int q) { if (timer) { long long now = clock64(); tacc[q] += now - tprev; tprev = now; } };
     // raw feature of a site for my image: pixel (in .x) or the precomputed phi; fetched TWO sites ahead so that the
     // load latency never meets the arithmetic that consumes it
-    auto load_raw = [&](int step) -> float2 {
-      if (!live || step >= nsteps) return make_float2(0.f, 0.f);
-      const float* fs = a.feat + feat_site_offset(a.fm, a.B, a.first + step * a.dir);
-      if (a.fm == TRMPS_FM_PRECOMPUTED) return __ldg(reinterpret_cast<const float2*>(fs) + t);
-      return make_float2(__ldg(fs + t), 0.f);
+    // running pointer to my feature of the site two steps ahead (one 64-bit add per step instead of a multiply)
+    const int64_t feat_stride = feat_site_offset(a.fm, a.B, 1) * a.dir;
+    const float* feat_ptr = a.feat + feat_site_offset(a.fm, a.B, a.first) + (a.fm == TRMPS_FM_PRECOMPUTED ? 2 : 1) * t;
+    int feat_step = 0;
+    auto load_raw = [&](int step) -> float2 {          // called with step = 0, 1, 2, ... in order
+      float2 r = make_float2(0.f, 0.f);
+      if (live && step < nsteps) {
+        if (a.fm == TRMPS_FM_PRECOMPUTED) r = __ldg(reinterpret_cast<const float2*>(feat_ptr));
+        else r.x = __ldg(feat_ptr);
+      }
+      feat_ptr += feat_stride;
+      ++feat_step;
+      return r;
     };
     auto phi_of_raw = [&](float2 raw) -> float2 {
       if (!live) return make_float2(0.f, 0.f);
@@ -448,7 +468,7 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(p0, __uint_as_float(x0[j]), p1 * __uint_as_float(x1[j]));
       };
-      if (a.dbg == 1 && !last) {
+      if (DBG && a.dbg == 1 && !last) {
         publish();
       } else if (last) {
         // final environment in fp32: undo both exponents
@@ -534,12 +554,22 @@ int launch_chain_kp(const ChainArgs& a, const float* nodes, uint8_t* img, int32_
     chain_prep_kernel<KP><<<296, 256, 0, st>>>(nodes, img, exps, a.Ds, a.first, a.dir, a.nsteps);
     TRMPS_LAUNCH_OK("chain_prep_kernel");
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    TRMPS_CUDA_OK(cudaFuncSetAttribute(chain_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem<KP>()));
-    attr_set = true;
+  const unsigned grid = (unsigned)ceil_div64(a.B, ChainCfg<KP>::TILES * CH_TM);
+  if (a.dbg != 0) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(chain_tc_kernel<KP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem<KP>()));
+      attr_set = true;
+    }
+    chain_tc_kernel<KP, true><<<grid, chain_threads<KP>(), chain_smem<KP>(), st>>>(a);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(chain_tc_kernel<KP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem<KP>()));
+      attr_set = true;
+    }
+    chain_tc_kernel<KP, false><<<grid, chain_threads<KP>(), chain_smem<KP>(), st>>>(a);
   }
-  chain_tc_kernel<KP><<<(unsigned)ceil_div64(a.B, ChainCfg<KP>::TILES * CH_TM), chain_threads<KP>(), chain_smem<KP>(), st>>>(a);
   TRMPS_LAUNCH_OK("chain_tc_kernel");
   return TRMPS_OK;
 }
