@@ -327,7 +327,9 @@ def run_ours(args, rank, local_rank, world):
     if not args.no_inference:
         del optim, st
         torch.cuda.empty_cache()
-        inference = inference_rate(N, D, args.inference_images_cfg3, "cfg3")
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        b3 = args.inference_images_cfg3 if args.inference_images_cfg3 > 0 else 3 * sms * 256
+        inference = inference_rate(N, D, b3, "cfg3")
         torch.cuda.empty_cache()
         inference_cfg5 = inference_rate(784, 32, args.inference_images, "cfg5")
     if rank != 0:
@@ -411,7 +413,8 @@ def main():
                     help="weak: --images-per-gpu images on every GPU (default); strong: that many images in total, sharded")
     ap.add_argument("--lr", type=float, default=1e-4, help="rate_of_change of the sweep (MPSTrainingParameters)")
     ap.add_argument("--inference-images", type=int, default=1000000, help="cfg5 images per GPU")
-    ap.add_argument("--inference-images-cfg3", type=int, default=120000, help="cfg3 (N=196, D=120) inference images per GPU")
+    ap.add_argument("--inference-images-cfg3", type=int, default=0,
+                    help="cfg3 (N=196, D=120) inference images per GPU; 0 = three full waves of the chain kernel (SMs x 256 images x 3)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

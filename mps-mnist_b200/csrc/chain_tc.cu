@@ -332,22 +332,25 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
             if (ev && k < 4) g_chain_dbg[17 + k] = (float)(clock64() - t_base);      // issued tile k
           }
         } else {
+          // Two tiles sharing a 3-stage ring.  Tile 0 runs two pieces ahead of tile 1,
+          //     (T0,p0) (T0,p1) (T1,p0) (T0,p2) (T1,p1) (T0,p3) (T1,p2) (T1,p3),
+          // which keeps at most two pieces live (+1 prefetch) and finishes tile 0 a third of a site before tile 1: the
+          // epilogue of tile 0 runs under the last MMAs of tile 1, the epilogue of tile 1 under the first of tile 0.
+          static_assert(C::TILE_MAJOR || (TILES == 2 && PIECES == 4), "staggered schedule is written for 2 tiles x 4 pieces");
+          constexpr int SK[8] = {0, 0, 1, 0, 1, 0, 1, 1}, SP[8] = {0, 1, 0, 2, 1, 3, 2, 3};
 #pragma unroll
-          for (int p = 0; p < PIECES; ++p) {
+          for (int i = 0; i < 8; ++i) {
+            const int k = SK[i], p = SP[i];
             const uint32_t q = (uint32_t)(s * PIECES + p), st = q % NSTAGE;
-            mbar_wait(&node_full[st], (q / NSTAGE) & 1u);
-            itick(0);
-#pragma unroll
-            for (int k = 0; k < TILES; ++k) {
-              if (p == 0) wait_a(k, s);
-              issue(k, p, st);
-              if (p == PIECES - 1) {
-                umma_commit(&x_ready[k]);
-                if (ev && k < 4) g_chain_dbg[17 + k] = (float)(clock64() - t_base);
-              }
-              itick(2);
+            if (k == 0) { mbar_wait(&node_full[st], (q / NSTAGE) & 1u); itick(0); }
+            if (p == 0) wait_a(k, s);
+            issue(k, p, st);
+            if (p == PIECES - 1) {
+              umma_commit(&x_ready[k]);
+              if (ev) g_chain_dbg[17 + k] = (float)(clock64() - t_base);
             }
-            umma_commit(&node_empty[st]);
+            if (k == 1) umma_commit(&node_empty[st]);
+            itick(2);
           }
         }
       }
