@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(ROOT, "mps-mnist_b200", "trmps")); sys.path.inse
 import numpy as np, torch
 import trmps_native as nat, trmps_device as dev
 from bench import synthetic_pixels, full_bond_mps
-N, B, L, D, loc = 16, 60000, 10, 120, 0
+N, B, L, D, loc = 12, 20000, 10, int(sys.argv[2]) if len(sys.argv) > 2 else 120, 0
 lr = float(sys.argv[1]) if len(sys.argv) > 1 else 1e-4
 pix, lab = synthetic_pixels(N, B, L, seed=100)
 nodes = full_bond_mps(N, 2, L, D, loc)
@@ -20,5 +20,5 @@ for c in range(N - 1):
     sv = np.sort(st.singular_values().cpu().numpy())[::-1]
     nrot = iw[8: 8 + ns]
     worst = iw[8 + 32: 8 + 32 + ns].view(np.float32)
-    print("bond %2d accept %d sweeps %2d  sigma[0,60,119,120,180,239] = %s" % (c, iw[0], ns, ["%.2e" % sv[i] for i in (0, 60, 119, 120, 180, min(239, len(sv) - 1))]))
+    print("bond %2d accept %d sweeps %2d  sigma[0,60,119,120,180,239] = %s" % (c, iw[0], ns, ["%.2e" % sv[min(i, len(sv) - 1)] for i in (0, D // 2, D - 1, D, 3 * D // 2, 2 * D - 1)]))
     print("    nrot  ", list(nrot)); print("    worst ", ["%.1e" % w for w in worst])
