@@ -30,7 +30,7 @@ constexpr int SVD_WARPS = SVD_THREADS / 32;
 
 struct SvdArgs {
   float* M; float* Ut; int R, Cc, Ds; const int32_t* d_near; int32_t* iscal; int32_t* rowmap; float* norms;
-  float tol; int max_sweeps; float* dbg;   // dbg: 8 floats, phase cycle counters of CTA 0 (load, gram, rotate, replay, store, grid sync)
+  float tol; int max_sweeps; int keep; float* dbg;   // keep: rows that can survive the truncation (max_size); dbg: 8 floats, phase cycle counters of CTA 0 (load, gram, rotate, replay, store, grid sync)
 };
 
 __device__ __forceinline__ int compact_to_row(int p, int dn, int Ds) { return (p / dn) * Ds + (p % dn); }
@@ -336,6 +336,7 @@ constexpr int CL_MAXU = 64;   // columns of U^T per CTA (R <= 512)
 
 struct SvdClArgs {
   SvdArgs a; int cols_per_cta; int ucols_per_cta; int32_t* flags;   // flags: [blocks][CL_SIZE] rounds completed
+  int32_t* wtop;     // [32] per-sweep worst |cos| (float bits) over pairs that involve a row that can survive the truncation
 };
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
@@ -394,7 +395,9 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
   __shared__ float rec_s[NR - 1][NP], rec_tau[NR - 1][NP];
   __shared__ int srow[NR], smrow[NR];
   __shared__ int sflag;
-  __shared__ float smax;
+  __shared__ float smax, smax_top, theta_s;
+  __shared__ int nbot_s;
+  __shared__ float cn_s[CL_SIZE * CL_MAXU];      // current squared norms by rank (R <= 512)
   __shared__ unsigned char tab_partner[2][NR - 1][NR], tab_first[2][NR - 1][NR], tab_pidx[2][NR - 1][NR];
   __shared__ unsigned char tab_x[2][NR - 1][NP], tab_y[2][NR - 1][NP];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -425,7 +428,28 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = timer ? clock64() : 0;
   auto tick = [&](int k) { if (timer) { long long now = clock64(); tacc[k] += now - tprev; tprev = now; } };
 
+  int32_t* wtop = ca.wtop;
   for (int sweep = 0; sweep < a.max_sweeps; ++sweep) {
+    // Rows whose squared norm is below 1/16 of the keep-th largest cannot survive the truncation (m <= max_size):
+    // pairs of two such rows do not count towards convergence.  Safety: with n_bot such rows and all their mutual
+    // cosines below w, their span has no singular value above sigma_keep * sqrt((1 + n_bot w) / 16), so the sweep
+    // loop may only stop on the kept rows' criterion while n_bot * w < 7 (nothing there can belong to the top m).
+    if (tid == 0) { theta_s = 0.f; nbot_s = 0; }
+    if (sweep > 0 && a.keep < Ra) {
+      for (int i = tid; i < Ra; i += CL_THREADS) cn_s[i] = __ldcg(&a.norms[i]);
+      __syncthreads();
+      for (int i = tid; i < Ra; i += CL_THREADS) {
+        const float c = cn_s[i];
+        int cnt = 0;
+        for (int o = 0; o < Ra; ++o) cnt += (cn_s[o] > c) || (cn_s[o] == c && o < i);
+        if (cnt == a.keep - 1) theta_s = 0.0625f * c;
+      }
+      __syncthreads();
+      int mine = 0;
+      for (int i = tid; i < Ra; i += CL_THREADS) mine += cn_s[i] < theta_s;
+      if (mine) atomicAdd(&nbot_s, mine);
+    }
+    __syncthreads();
     for (int r = 0; r < rounds; ++r, ++ground) {
       if (!active) continue;
       int bi, bj;
@@ -439,7 +463,7 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
         smrow[tid] = ok ? __ldcg(&a.rowmap[p]) : 0;
       }
       if (tid == 0) {
-        sflag = 0; smax = 0.f;
+        sflag = 0; smax = 0.f; smax_top = 0.f;
         // wait until the previous holders of my two blocks (same column slice) have stored them
         if (bi < nb) while (ld_volatile(&ca.flags[bi * CL_SIZE + crank]) < ground) { }
         if (bj < nb) while (ld_volatile(&ca.flags[bj * CL_SIZE + crank]) < ground) { }
@@ -511,6 +535,7 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
         const int y = x + rem;
         Gs[0][x][y] = s;
         Gs[0][y][x] = s;
+        if (x == y && crank == 0 && srow[x] >= 0) a.norms[srow[x]] = s;      // current squared norm, by rank
       }
       __syncthreads();
       tick(1);
@@ -521,7 +546,8 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
       int cur = 0;
       {
         const int i = tid / NR, j = tid % NR, pl = lane & 7;
-        float worst_rel = 0.f;
+        float worst_rel = 0.f, worst_top = 0.f;
+        const float theta = theta_s;
         // pairing data of the step (constant tables): fetched one step ahead, off the critical path
         int px = tab_x[all][0][pl], py = tab_y[all][0][pl];
         int qi = tab_pidx[all][0][i], qj = tab_pidx[all][0][j];
@@ -554,11 +580,13 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
             rec_tau[step][tid] = tau;
             if (rot) sflag = 1;
             worst_rel = fmaxf(worst_rel, relg);
+            if (fmaxf(al, be) >= theta) worst_top = fmaxf(worst_top, relg);
           }
           __syncthreads();
           cur ^= 1;
         }
         if (tid < NP && worst_rel > 0.f) atomicMax(reinterpret_cast<int*>(&smax), __float_as_int(worst_rel));
+        if (tid < NP && worst_top > 0.f) atomicMax(reinterpret_cast<int*>(&smax_top), __float_as_int(worst_top));
         __syncthreads();
       }
       tick(2);
@@ -605,6 +633,7 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
         if (tid == 0 && crank == 0) {
           atomicAdd(&a.iscal[TRMPS_I_SVD_ROT + sweep], 1);
           atomicMax(&a.iscal[TRMPS_I_SVD_ROT + 32 + (sweep & 31)], __float_as_int(smax));
+          atomicMax(&wtop[sweep & 31], __float_as_int(smax_top));
         }
       }
       // ---- publish: my slice of both blocks is up to date for round ground+1 (the barrier orders every thread's
@@ -622,7 +651,9 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
     sweeps_used = sweep + 1;
     const int nrot = __ldcg(&a.iscal[TRMPS_I_SVD_ROT + sweep]);
     const float worst = __int_as_float(__ldcg(&a.iscal[TRMPS_I_SVD_ROT + 32 + (sweep & 31)]));
-    if (nrot == 0 || worst < 1e-3f) break;     // quadratic convergence: what is left is O(worst^2) <= 1e-6
+    const float worst_kept = __int_as_float(__ldcg(&wtop[sweep & 31]));
+    // quadratic convergence: what is left after this sweep is O(worst^2) <= 1e-6
+    if (nrot == 0 || worst < 1e-3f || (worst_kept < 1e-3f && worst * (float)nbot_s < 7.f)) break;
   }
   if (blockIdx.x == 0 && tid == 0) {
     a.iscal[TRMPS_I_SVD_SWEEPS] = sweeps_used;
@@ -772,6 +803,7 @@ int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, 
   a.rowmap = reinterpret_cast<int32_t*>(s->work + lay.sv + 2 * R);
   a.tol = 5.9604645e-8f * sqrtf((float)Cc);
   a.dbg = s->work + lay.red;
+  a.keep = opt->max_size < Ds ? opt->max_size : Ds;
   a.max_sweeps = opt->max_svd_sweeps > 0 ? (opt->max_svd_sweeps < 30 ? opt->max_svd_sweeps : 30) : 30;
   svd_norms_kernel<<<(R * 32 + 255) / 256, 256, 0, st>>>(a);
   TRMPS_LAUNCH_OK("svd_norms_kernel");
@@ -791,10 +823,11 @@ int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, 
     ca.flags = reinterpret_cast<int32_t*>(s->work + lay.red + 32);
     const int slots = (ca.cols_per_cta + CL_THREADS - 1) / CL_THREADS;
     const int nbk = (R + CL_NR / 2 - 1) / (CL_NR / 2);
+    ca.wtop = ca.flags + (nbk + 1) * CL_SIZE;
     const int ncl = ((nbk + (nbk & 1)) / 2) > 1 ? (nbk + (nbk & 1)) / 2 : 1;
     static bool cluster_ok = true;
     if (cluster_ok && slots <= 4 && ca.ucols_per_cta <= CL_MAXU && (nbk + 1) * CL_SIZE <= 2048) {
-      svd_zero_flags_kernel<<<((nbk + 1) * CL_SIZE + 255) / 256, 256, 0, st>>>(ca.flags, (nbk + 1) * CL_SIZE);
+      svd_zero_flags_kernel<<<((nbk + 1) * CL_SIZE + 40 + 255) / 256, 256, 0, st>>>(ca.flags, (nbk + 1) * CL_SIZE + 40);
       TRMPS_LAUNCH_OK("svd_zero_flags_kernel");
       cudaError_t e = slots <= 1 ? launch_jacobi_cluster<1>(ca, ncl, st)
                     : slots <= 2 ? launch_jacobi_cluster<2>(ca, ncl, st)

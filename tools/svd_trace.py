@@ -22,3 +22,7 @@ for c in range(N - 1):
     worst = iw[8 + 32: 8 + 32 + ns].view(np.float32)
     print("bond %2d accept %d sweeps %2d  sigma[0,60,119,120,180,239] = %s" % (c, iw[0], ns, ["%.2e" % sv[min(i, len(sv) - 1)] for i in (0, D // 2, D - 1, D, 3 * D // 2, 2 * D - 1)]))
     print("    nrot  ", list(nrot)); print("    worst ", ["%.1e" % w for w in worst])
+    R = 2 * st.Ds; nbk = (R + 7) // 8
+    off = st.layout.red + 32 + (nbk + 1) * 8
+    wt = st.work[off: off + ns].cpu().numpy().view(np.float32)
+    print("    w_top ", ["%.1e" % w for w in wt])
