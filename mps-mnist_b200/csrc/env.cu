@@ -343,7 +343,7 @@ extern "C" int trmps_predict(const trmps_predict_desc* p, void* stream) {
     if ((rc = launch_chain_tc(p->feat, fm, B, Ds, L, p->nodes, 0, +1, p->loc, 0, img, buf[0], st))) return rc;
     if ((rc = launch_chain_tc(p->feat, fm, B, Ds, L, p->nodes, N - 1, -1, N - 1 - p->loc, 1, img, buf[2], st))) return rc;
     if ((rc = trmps::launch_phi_site(p->feat + feat_site_offset(fm, B, p->loc), fm, B, phi_loc, st))) return rc;
-    if (option_value(1) == 0 && forward_tc_supported(Ds, L, 2)) {
+    if (option_value(1) != 1 && forward_tc_supported(Ds, L, 2)) {
       // special-node contraction (mps.py:552-557) on the tensor cores: a bond whose far site is the identity
       float* M2 = img + chain_tc_image_floats(Ds, N);
       M2 += (256 - ((uintptr_t)M2 / sizeof(float)) % 256) % 256;

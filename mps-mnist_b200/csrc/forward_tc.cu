@@ -15,6 +15,7 @@
 // Warp roles (192 threads): warps 0-3 epilogue (one TMEM lane quadrant each), warp 4 issues the MMAs, warp 5
 // streams the B images with cp.async.bulk into a 3-stage mbarrier ring.  The accumulator is double buffered in
 // TMEM so the epilogue of tile j overlaps the MMAs of tile j+1.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace trmps {
@@ -281,6 +282,232 @@ __global__ void __launch_bounds__(FT_THREADS, 1) forward_tc_kernel(FwdTcArgs a) 
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// =====================================================================================================
+// fp16 hi/lo variant (kind::f16): the same contraction with both operands carried as two fp16 halves,
+//     x = 2^e (h + l),  products h.h + l.h + h.l  (22 mantissa bits, like 3xTF32),
+// at twice the TF32 rate (tools/probe/f16_probe.cu: an M=128 tcgen05.mma costs N/2 cycles for K=8 TF32 and for
+// K=16 fp16 alike).  Exponents: one per image row of e_near (row maximum scaled into [2^12, 2^13)), one for the whole
+// bond matrix (maximum into [2^13, 2^14)); both are exact powers of two and are undone in FP32 in the epilogue.
+// Both operands K-major SWIZZLE_128B: A = [hi|lo][k atom][128 rows x 128 B], B image of (tile j, chunk q) =
+// [hi|lo][160 rows (k_local; l,m,n) x 64 near-bond indices].
+constexpr int FH_TROW = 12, FH_TB = 13;
+constexpr int FH_A_BYTES = 4 * 16384;                       // hi ka0, hi ka1, lo ka0, lo ka1
+constexpr int FH_KCH = 64;                                  // near-bond indices per B stage
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__host__ __device__ __forceinline__ uint32_t k128_chunk_off(int r, int ch) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((ch ^ r) & 7) << 4));
+}
+__device__ __forceinline__ float pow2f(int e) { return __int_as_float((e + 127) << 23); }     // -126 <= e <= 127
+__device__ __forceinline__ int exponent_of(float x) { return (int)((__float_as_uint(x) >> 23) & 0xffu) - 127; }
+__device__ __forceinline__ float scale_pow2(float x, int e) {
+  e = max(-250, min(250, e));
+  const int e1 = e / 2;
+  return x * pow2f(e1) * pow2f(e - e1);
+}
+
+// max |M| as the bit pattern of a non-negative float (integer max is order preserving); *out zeroed by the caller
+__global__ void absmax_kernel(const float* __restrict__ M, int64_t n, int32_t* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(M[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_int(m));
+}
+__device__ __forceinline__ int bond_exponent(const int32_t* maxbits) {
+  const float m = __int_as_float(__ldg(maxbits));
+  return (m > 0.f && m < 3.0e38f) ? exponent_of(m) - FH_TB : 0;
+}
+
+// bond matrix -> fp16 hi/lo images [tile j][chunk q][hi|lo][160 rows x 128 B]; one thread per (row, 8 near-bond indices)
+template <int L>
+__global__ void forward_prep_h_kernel(const float* __restrict__ M, uint8_t* __restrict__ bimg, const int32_t* __restrict__ maxbits,
+                                      int Ds, int ntiles, int nchunks) {
+  constexpr int NT = 16 * L, IMG_BYTES = NT * 128;
+  const int64_t Cc = (int64_t)2 * L * Ds;
+  const int ex = -bond_exponent(maxbits);
+  const int64_t total = (int64_t)ntiles * nchunks * NT * 8;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % 8);
+    const int col = (int)((e / 8) % NT);
+    const int64_t jq = e / (8 * NT);
+    const int q = (int)(jq % nchunks), j = (int)(jq / nchunks);
+    const int kl = col / (4 * L), r = col % (4 * L), l = r >> 2, m = (r >> 1) & 1, n = r & 1;
+    const int k = 4 * j + kl;
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = q * FH_KCH + ch * 8 + u;
+      float v = 0.f;
+      if (k < Ds && i < Ds) v = M[(int64_t)(m * Ds + i) * Cc + (int64_t)(l * 2 + n) * Ds + k];
+      v = scale_pow2(v, ex);
+      hi[u] = __float2half_rn(v);
+      lo[u] = __float2half_rn(v - __half2float(hi[u]));
+    }
+    uint8_t* img = bimg + jq * (2 * IMG_BYTES) + k128_chunk_off(col, ch);
+    *reinterpret_cast<uint4*>(img) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(img + IMG_BYTES) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+struct FwdHArgs {
+  const float* e_near; const float* e_far; const float* phi_near; const float* phi_far; const uint8_t* bimg;
+  const int32_t* maxbits; float* f; int64_t B; int Ds; const int32_t* d_near; const int32_t* d_far; int nchunks_max;
+};
+
+template <int L>
+__global__ void __launch_bounds__(FT_THREADS, 1) forward_h_kernel(FwdHArgs a) {
+  constexpr int NT = 16 * L;
+  constexpr int IMG_BYTES = NT * 128;                // one (hi | lo) B image: NT rows x 64 fp16
+  constexpr int STAGE_BYTES = 2 * IMG_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * NT <= 64 ? 64 : 2 * NT <= 128 ? 128 : 2 * NT <= 256 ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_t = smem;
+  uint8_t* bst = smem + FH_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bst + FT_STAGES * STAGE_BYTES);
+  uint64_t* b_full = bars, *b_empty = bars + FT_STAGES, *acc_full = bars + 2 * FT_STAGES, *acc_empty = bars + 2 * FT_STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FT_STAGES + 4);
+  int* rexp = reinterpret_cast<int*>(bars + 2 * FT_STAGES + 6);      // [128] row exponents
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Ds = a.Ds;
+  const int64_t t0 = (int64_t)blockIdx.x * FT_TM;
+  const int dn = __ldg(a.d_near), df = __ldg(a.d_far);
+  const int nchunks = (dn + FH_KCH - 1) / FH_KCH;
+  const int ntiles = (df + 3) / 4;
+
+  if (tid == 0) {
+    for (int s = 0; s < FT_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+
+  // ---- A tile: one image row per warp iteration (lane = 4 consecutive k), row maximum by shuffle, scaled fp16 hi/lo
+  for (int t = warp; t < FT_TM; t += FT_THREADS / 32) {
+    const int64_t tg = t0 + t;
+    const int k = 4 * lane;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tg < a.B && k < Ds) v = __ldg(reinterpret_cast<const float4*>(a.e_near + tg * Ds + k));
+    float mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const int ex = (mx > 0.f && mx < 3.0e38f) ? exponent_of(mx) - FH_TROW : 0;
+    if (lane == 0) rexp[t] = ex;
+    if (k < nchunks * FH_KCH) {
+      const float x0 = scale_pow2(v.x, -ex), x1 = scale_pow2(v.y, -ex), x2 = scale_pow2(v.z, -ex), x3 = scale_pow2(v.w, -ex);
+      const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+      const uint32_t off = (uint32_t)((k >> 6) * 16384) + k128_chunk_off(t, (k & 63) >> 3) + (uint32_t)((lane & 1) * 8);
+      uint2 hv, lv;
+      hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+      lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+      *reinterpret_cast<uint2*>(a_t + off) = hv;
+      *reinterpret_cast<uint2*>(a_t + 2 * 16384 + off) = lv;
+    }
+  }
+  fence_async_proxy();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    if (lane == 0) {
+      int it = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        for (int q = 0; q < nchunks; ++q, ++it) {
+          const int s = it % FT_STAGES, ph = (it / FT_STAGES) & 1;
+          if (it >= FT_STAGES) mbar_wait(&b_empty[s], (uint32_t)(ph ^ 1));
+          mbar_expect_tx(&b_full[s], STAGE_BYTES);
+          bulk_g2s(bst + s * STAGE_BYTES, a.bimg + ((int64_t)j * a.nchunks_max + q) * STAGE_BYTES, STAGE_BYTES, &b_full[s]);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      // kind::f16, fp16 x fp16 -> fp32, both K-major, N = NT, M = 128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(FT_TM >> 4) << 24);
+      const uint64_t adesc0 = make_desc(smem_u32(a_t), 16, 1024, 2), bdesc0 = make_desc(smem_u32(bst), 16, 1024, 2);
+      int it = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        const int b = j & 1;
+        if (j >= 2) mbar_wait(&acc_empty[b], (uint32_t)(((j >> 1) - 1) & 1));
+        tc_fence_after();
+        const uint32_t d = tmem_base + b * NT;
+        for (int q = 0; q < nchunks; ++q, ++it) {
+          const int s = it % FT_STAGES, ph = (it / FT_STAGES) & 1;
+          mbar_wait(&b_full[s], (uint32_t)ph);
+          tc_fence_after();
+          // descriptor addresses in 16-byte units: +2 per K=16 step, +1024 per 16 KB atom of A, lo halves 2 atoms / one image on
+          const uint64_t ahi = adesc0 + (uint64_t)(q * 1024), alo = ahi + 2048;
+          const uint64_t bhi = bdesc0 + (uint64_t)(s * (STAGE_BYTES >> 4)), blo = bhi + (IMG_BYTES >> 4);
+          const int ksteps = min(4, (dn - q * FH_KCH + 15) / 16);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            umma_f16(d, ahi + 2 * ks, bhi + 2 * ks, idesc, (q > 0 || ks > 0) ? 1u : 0u);
+            umma_f16(d, alo + 2 * ks, bhi + 2 * ks, idesc, 1u);
+            umma_f16(d, ahi + 2 * ks, blo + 2 * ks, idesc, 1u);
+          }
+          umma_commit(&b_empty[s]);
+        }
+        umma_commit(&acc_full[b]);
+      }
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const int64_t tg = t0 + row;
+    const bool live = tg < a.B;
+    float pp[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      const float2 p1 = __ldg(reinterpret_cast<const float2*>(a.phi_near) + tg);
+      const float2 p2 = __ldg(reinterpret_cast<const float2*>(a.phi_far) + tg);
+      pp[0] = p1.x * p2.x; pp[1] = p1.x * p2.y; pp[2] = p1.y * p2.x; pp[3] = p1.y * p2.y;   // index m*2+n
+    }
+    float facc[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) facc[l] = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      const int b = j & 1;
+      float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live && 4 * j < Ds) e4 = __ldg(reinterpret_cast<const float4*>(a.e_far + tg * Ds + 4 * j));
+      const float ek[4] = {e4.x, e4.y, e4.z, e4.w};
+      mbar_wait(&acc_full[b], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int cb = 0; cb < NT / 32; ++cb) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * NT + cb * 32), v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int col = cb * 32 + e;                       // compile-time: (k_local; l, m, n)
+          const int kl = col / (4 * L), r = col % (4 * L), l = r >> 2, mn = r & 3;
+          facc[l] = fmaf(v[e], pp[mn] * ek[kl], facc[l]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+    }
+    if (live) {
+      const int ex = rexp[row] + bond_exponent(a.maxbits);       // undo both scalings (exact powers of two)
+#pragma unroll
+      for (int l = 0; l < L; ++l) a.f[tg * L + l] = scale_pow2(facc[l], ex);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int L>
+size_t forward_h_smem() { return (size_t)FH_A_BYTES + (size_t)FT_STAGES * 2 * 16 * L * 128 + 1024 + 1024; }
+
 template <int L>
 size_t forward_tc_smem() { return (size_t)2 * FT_A_BYTES + (size_t)FT_STAGES * 2 * 16 * 16 * L * 4 + 256 + 1024; }
 
@@ -291,7 +518,7 @@ bool forward_tc_supported(int Ds, int L, int nd) { return nd == 2 && L == 10 && 
 // floats needed for the hi/lo B images of one bond
 int64_t forward_tc_image_floats(int Ds, int L) {
   const int64_t ntiles = (Ds + 3) / 4, nchunks = (Ds + FT_KCH - 1) / FT_KCH;
-  return ntiles * nchunks * 2 * 16 * 16 * L;
+  return ntiles * nchunks * 2 * 16 * 16 * L + 64;      // the fp16 images need half of this; + the bond exponent word
 }
 
 int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_near, const float* phi_far, const float* M,
@@ -301,6 +528,29 @@ int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_
   if (!forward_tc_supported(Ds, L, 2)) {
     set_error("forward_tc: unsupported shape Ds=%d L=%d", Ds, L);
     return TRMPS_E_ARG;
+  }
+  if (option_value(1) == 0) {
+    // fp16 hi/lo operands (default)
+    const int ntiles = (Ds + 3) / 4, nchunks = (Ds + FH_KCH - 1) / FH_KCH;
+    uint8_t* img = reinterpret_cast<uint8_t*>(bimg);
+    int32_t* maxbits = reinterpret_cast<int32_t*>(img + (size_t)ntiles * nchunks * 2 * 16 * L * 128);
+    TRMPS_CUDA_OK(cudaMemsetAsync(maxbits, 0, sizeof(int32_t), st));
+    absmax_kernel<<<148, 256, 0, st>>>(M, (int64_t)2 * Ds * 2 * L * Ds, maxbits);
+    TRMPS_LAUNCH_OK("absmax_kernel");
+    forward_prep_h_kernel<10><<<592, 256, 0, st>>>(M, img, maxbits, Ds, ntiles, nchunks);
+    TRMPS_LAUNCH_OK("forward_prep_h_kernel");
+    FwdHArgs h;
+    h.e_near = e_near; h.e_far = e_far; h.phi_near = phi_near; h.phi_far = phi_far; h.bimg = img; h.maxbits = maxbits;
+    h.f = f_out; h.B = B; h.Ds = Ds; h.d_near = d_near; h.d_far = d_far; h.nchunks_max = nchunks;
+    const size_t smem_h = forward_h_smem<10>();
+    static bool attr_h = false;
+    if (!attr_h) {
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(forward_h_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+      attr_h = true;
+    }
+    forward_h_kernel<10><<<(unsigned)ceil_div64(B, FT_TM), FT_THREADS, smem_h, st>>>(h);
+    TRMPS_LAUNCH_OK("forward_h_kernel");
+    return TRMPS_OK;
   }
   const int ntiles = (Ds + 3) / 4, nchunks = (Ds + FT_KCH - 1) / FT_KCH;
   forward_prep_kernel<10><<<592, 256, 0, st>>>(M, bimg, Ds, ntiles, nchunks);

@@ -104,7 +104,7 @@ static int compute_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, int32_t s
     if (eff > best_eff + 1e-9) { best_eff = eff; best = ns; }
     if (eff >= 0.9) { best = ns; break; }
   }
-  const bool fwd_tc = g_fwd_impl == 0 && forward_tc_supported(Ds, L, 2);
+  const bool fwd_tc = g_fwd_impl != 1 && forward_tc_supported(Ds, L, 2);
   if (fwd_tc) best = 1;      // the tensor-core forward writes complete logits
   int64_t off = 0;
   o->bondM = off; off += a4(RC);
@@ -198,7 +198,7 @@ static int do_merge(const trmps_sweep* s, const trmps_layout& lay, const BondGeo
 static int do_forward(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const float* M, cudaStream_t st) {
   ProfScope ps(PROF_FORWARD, st);
   const float* phi2 = s->work + lay.phi2;
-  if (g_fwd_impl == 0 && forward_tc_supported(s->Ds, s->L, 2))
+  if (g_fwd_impl != 1 && forward_tc_supported(s->Ds, s->L, 2))
     return launch_forward_tc(g.e_near, g.e_far, phi2, phi2 + 2 * s->B, M, s->work + lay.bimg, s->work + lay.fpart, s->B, s->Ds,
                              s->L, g.d_near, g.d_far, st);
   return launch_forward(g.e_near, g.e_far, phi2, phi2 + 2 * s->B, M, s->work + lay.fpart, lay.nsplit, s->B, s->Ds, s->L, 2,
@@ -382,7 +382,7 @@ extern "C" int64_t trmps_launch_count(void) { return (int64_t)g_launches; }
 
 extern "C" int trmps_set_option(int32_t option, int32_t value) {
   if (option == 0 && (value == 0 || value == 1)) { g_grad_impl = value; return TRMPS_OK; }
-  if (option == 1 && (value == 0 || value == 1)) { g_fwd_impl = value; return TRMPS_OK; }
+  if (option == 1 && (value == 0 || value == 1 || value == 2)) { g_fwd_impl = value; return TRMPS_OK; }
   if (option == 2 && (value == 0 || value == 1)) { g_chain_impl = value; return TRMPS_OK; }
   set_error("trmps_set_option: unknown option %d / value %d", option, value);
   return TRMPS_E_ARG;

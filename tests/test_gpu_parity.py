@@ -391,7 +391,7 @@ def test_tcgen05_forward_matches_simt_and_fp64(D, B, direction):
     pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=71, fm=o.FM_COS_SIN, full_bond=D, loc=loc)
     results = {}
     try:
-        for impl in (nat.FWD_SIMT, nat.FWD_TCGEN05):
+        for impl in (nat.FWD_SIMT, nat.FWD_TCGEN05, nat.FWD_TCGEN05_TF32):
             nat.set_option(nat.OPT_FWD_IMPL, impl)
             st = make_state(N, B, L, D, nodes, loc, phi, lab)       # layout (nsplit) depends on the option
             st.init_env(loc)
@@ -410,6 +410,7 @@ def test_tcgen05_forward_matches_simt_and_fp64(D, B, direction):
     f64 = o.forward_factored(bond.astype(np.float64), Cn.astype(np.float64), Cf.astype(np.float64), pn.astype(np.float64), pf.astype(np.float64))
     assert rel(results[nat.FWD_SIMT], f64) < 1e-5
     assert rel(results[nat.FWD_TCGEN05], f64) < 1e-5
+    assert rel(results[nat.FWD_TCGEN05_TF32], f64) < 1e-5
     assert np.array_equal(results[nat.FWD_TCGEN05].argmax(1), f64.argmax(1)) or rel(results[nat.FWD_TCGEN05], f64) < 1e-6
 
 
