@@ -691,23 +691,32 @@ struct SvdFinArgs {
   float min_sv; int max_size, min_size;
 };
 
+// squared norms of the converged rows, one warp per Jacobi rank (the whole grid reads the 2.4 MB bond; a single CTA
+// took 48 us for it)
+__global__ void svd_rank_norms_kernel(const float* __restrict__ M, const int32_t* __restrict__ rowmap, const int32_t* __restrict__ d_near,
+                                      int Cc, float* __restrict__ out) {
+  const int Ra = 2 * *d_near, lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int p = gw; p < Ra; p += nw) {
+    const float4* row = reinterpret_cast<const float4*>(M + (size_t)rowmap[p] * Cc);
+    float s = 0.f;
+    for (int c4 = lane; c4 < Cc / 4; c4 += 32) {
+      float4 v = row[c4];
+      s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[p] = s;
+  }
+}
+
 __global__ void __launch_bounds__(1024) svd_finalize_kernel(SvdFinArgs a) {
   extern __shared__ float sig[];   // [R]
   __shared__ int s_count;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int dn = *a.d_near, Ra = 2 * dn;
   if (tid == 0) s_count = 0;
-  for (int p = w; p < Ra; p += 32) {
-    const float4* row = reinterpret_cast<const float4*>(a.M + (size_t)a.rowmap[p] * a.Cc);
-    float s = 0.f;
-    for (int c4 = lane; c4 < a.Cc / 4; c4 += 32) {
-      float4 v = row[c4];
-      s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) sig[p] = sqrtf(s);
-  }
+  for (int p = tid; p < Ra; p += 1024) sig[p] = sqrtf(a.sv[p]);      // squared row norms by Jacobi rank (svd_rank_norms_kernel)
   __syncthreads();
   const int kmax = min(Ra, 2 * a.L * (*a.d_far));
   int local = 0;
@@ -867,6 +876,8 @@ int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, 
   f.min_sv = opt->min_singular_value;
   f.max_size = opt->max_size < Ds ? opt->max_size : Ds;
   f.min_size = opt->min_size > 0 ? opt->min_size : 3;
+  svd_rank_norms_kernel<<<(R * 32 + 255) / 256, 256, 0, st>>>(a.M, a.rowmap, a.d_near, Cc, f.sv);
+  TRMPS_LAUNCH_OK("svd_rank_norms_kernel");
   svd_finalize_kernel<<<1, 1024, R * sizeof(float), st>>>(f);
   TRMPS_LAUNCH_OK("svd_finalize_kernel");
 
