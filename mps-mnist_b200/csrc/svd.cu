@@ -356,25 +356,31 @@ __device__ __forceinline__ void pair_of_row(int all, int step, int row, int& x, 
   else { pidx = (NR - 1) - j; y = row; x = (step + pidx) % (NR - 1); }
 }
 
+__device__ __forceinline__ float rsqrt_fast(float x) {      // one MUFU.RSQ, no denormal fix-up (callers keep x in range)
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // rotation that annihilates the (x,y) entry of a 2x2 Gram [[al, ga],[ga, be]]: x' = c x - s y, y' = s x + c y.
-// Half-angle form: cos 2t = |be-al| / hyp, sin 2t = sgn * 2|ga| / hyp, c = sqrt((1 + cos 2t)/2), s = sin 2t / (2c);
-// three dependent special-function ops (rsqrt, rsqrt, rcp) instead of six, no divergent branches.
+// Half-angle form on the NORMALISED Gram (divide by sqrt(al be): no exponent juggling, nothing can over- or
+// underflow while the pair is rotated at all): cos 2t = |d| / hyp, sin 2t = sgn * 2|g| / hyp with
+// d = (be - al) / sqrt(al be), g = ga / sqrt(al be), c = sqrt((1 + cos 2t)/2), s = sin 2t / (2c).
+// The dependent chain is rsqrt -> 2 mul -> fma -> rsqrt -> mul -> fma -> rsqrt -> 2 mul (~110 cycles; the previous
+// form with exponent arithmetic and IEEE-range rsqrtf took 250, tools/probe/rot_probe.cu).
 __device__ __forceinline__ bool rotation_params(float al, float be, float ga, float tol, float& c, float& s, float& tau, float& relg) {
   const float big = fmaxf(al, be), small = fminf(al, be);
-  relg = fabsf(ga) * rsqrtf(al) * rsqrtf(be);
+  const float rr = rsqrt_fast(al) * rsqrt_fast(be);
+  const float g = ga * rr;                                      // cosine of the angle between the rows
+  relg = fabsf(g);
   const bool rot = small > 1e-30f && small > 1e-24f * big && relg > tol;
-  // scale by a power of two near 1/max(al,be) (exponent arithmetic, no special-function op) so that the squares
-  // below neither underflow for tiny rows nor overflow for huge ones
-  const int ebig = (__float_as_int(big) >> 23) & 0xff;
-  const float scale = __int_as_float(max(1, min(253, 254 - ebig)) << 23);
-  const float d = (be - al) * scale, gs = ga * scale;
-  const float rh = rsqrtf(fmaxf(fmaf(d, d, 4.f * gs * gs), 1e-37f));   // 1 / hyp
+  const float d = (be - al) * rr;                               // |d| <= sqrt(big / small) <= 1e12 when rot
+  const float rh = rsqrt_fast(fmaf(d, d, 4.f * g * g));        // 1 / hyp
   const float c2 = fabsf(d) * rh;                               // cos 2t  (>= 0)
   const float x = fmaf(0.5f, c2, 0.5f);                         // cos^2 t in [0.5, 1]
-  const float rc = rsqrtf(x);                                   // 1 / c
+  const float rc = rsqrt_fast(x);                               // 1 / c
   const float cc = x * rc;
-  const float sg = (d >= 0.f) ? 1.f : -1.f;
-  const float ss = sg * gs * rh * rc;                           // sin 2t / (2 c), sin 2t = sg * 2 ga / hyp
+  const float ss = ((d >= 0.f) ? g : -g) * rh * rc;             // sin 2t / (2 c), sin 2t = sgn * 2 g / hyp
   c = rot ? cc : 1.f;
   s = rot ? ss : 0.f;
   tau = rot ? __fdividef(ss, 1.f + cc) : 0.f;
