@@ -460,3 +460,28 @@ def test_fused_chain_tracks_exponents_over_wild_scales(D):
     # hi + lo fp16 carries 22 mantissa bits (as 3xTF32 does): a few times the FP32 rounding error, well inside 1e-4
     assert rel(got, want) < 5e-5
     assert rel(simt, want) < 1e-5
+
+
+@pytest.mark.parametrize("scale", [0.0, 1e-25, 1e18])
+def test_fp16_forward_is_scale_invariant(scale):
+    """forward_h carries one power-of-two exponent for the bond and one per image row of the environment: the logits of
+    a bond scaled by any representable factor must be the scaled logits (exactly, for powers of two; to rounding
+    otherwise), and an all-zero bond (a zero Armijo direction) must give zeros, not NaNs."""
+    N, B, L, D, loc = 6, 900, 10, 56, 2
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=73, fm=o.FM_COS_SIN, full_bond=D, loc=loc)
+    st = make_state(N, B, L, D, nodes, loc, phi, lab)
+    st.init_env(loc)
+    st.bond_merge(loc, +1)
+    st.bond_forward(loc, +1, 0)
+    base = st.logits0().clone()
+    st.bond_matrix().mul_(scale)
+    st.envL[loc].mul_(3.0)                   # row scaling of the near environment as well
+    st.bond_forward(loc, +1, 0)
+    torch.cuda.synchronize()
+    got = st.logits0().cpu().numpy()
+    want = base.cpu().numpy().astype(np.float64) * (np.float64(np.float32(scale)) * 3.0)
+    assert np.isfinite(got).all()
+    if scale == 0.0:
+        assert np.all(got == 0)
+    else:
+        assert rel(got, want) < 2e-6
