@@ -485,3 +485,30 @@ def test_fp16_forward_is_scale_invariant(scale):
         assert np.all(got == 0)
     else:
         assert rel(got, want) < 2e-6
+
+
+@pytest.mark.parametrize("L,D", [(3, 24), (16, 40)])
+def test_other_label_counts(L, D):
+    """d_output != 10 (the tensor-core contractions are specialised for 10 labels): predict and a full bond update
+    through the general kernels against the oracle."""
+    N, B, loc = 9, 400, 3
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=17, fm=o.FM_COS_SIN, full_bond=D, loc=loc)
+    w = dev.DeviceWeights(nodes, loc, L, dev.bond_stride(nodes, loc, L), cuda())
+    got = dev.predict(w, torch.from_numpy(pix).cuda(), nat.FM_COS_SIN).cpu().numpy()
+    want = o.predict([n.astype(np.float64) for n in nodes], loc, phi.astype(np.float64), L)
+    assert rel(got, want) < 2e-5
+    # one bond update to the right
+    p = o.SweepParams(max_size=D)
+    tr = o.Trace()
+    C1s, C2s = o.setup_environments(nodes, loc, phi, L)
+    a_j, n1 = o.update_right(loc, nodes[loc], list(nodes), C1s, C2s, phi, lab, 0.05, p, tr)
+    st = make_state(N, B, L, D, nodes, loc, phi, lab)
+    st.init_env(loc)
+    st.bond_step(loc, +1, dev.make_opt(lr=0.05, max_size=D))
+    torch.cuda.synchronize()
+    iw, sc = st.iwork.cpu().numpy(), st.scalars().cpu().numpy()
+    assert int(iw[nat.I_M]) == tr[0]["m"]
+    assert int(iw[nat.I_ACCEPT]) == int(tr[0]["accepted"])
+    assert abs(sc[0] - tr[0]["cost0"]) < 1e-4 * abs(tr[0]["cost0"])
+    sv = np.sort(st.singular_values().cpu().numpy())[::-1][:tr[0]["m"]]
+    assert rel(sv, tr[0]["s"][:tr[0]["m"]]) < 1e-4
