@@ -16,6 +16,7 @@
 // streams the B images with cp.async.bulk into a 3-stage mbarrier ring.  The accumulator is double buffered in
 // TMEM so the epilogue of tile j overlaps the MMAs of tile j+1.
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace trmps {
@@ -359,12 +360,46 @@ struct FwdHArgs {
   const int32_t* maxbits; float* f; int64_t B; int Ds; const int32_t* d_near; const int32_t* d_far; int nchunks_max;
 };
 
+constexpr int FH_THREADS = 320;        // warps 0-7: epilogue (TMEM lane quadrant x column half), 8: MMA issuer, 9: B loader
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// one accumulator tile, my half of its columns (16-column chunks [HALF*NCH, (HALF+1)*NCH)): every column has a
+// compile-time (k_local; l, m, n)
+template <int L, int HALF>
+__device__ __forceinline__ void fh_epilogue_tile(uint32_t taddr, const float (&pp)[4], const float (&ek)[4], float (&facc)[L]) {
+  constexpr int NCH = (16 * L) / 32;          // 16-column chunks per half
+#pragma unroll
+  for (int cb = 0; cb < NCH; ++cb) {
+    float v[16];
+    tmem_ld16(taddr + (uint32_t)((HALF * NCH + cb) * 16), v);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int col = (HALF * NCH + cb) * 16 + e;
+      const int kl = col / (4 * L), r = col % (4 * L), l = r >> 2, mn = r & 3;
+      facc[l] = fmaf(v[e], pp[mn] * ek[kl], facc[l]);
+    }
+  }
+}
+
 template <int L>
-__global__ void __launch_bounds__(FT_THREADS, 1) forward_h_kernel(FwdHArgs a) {
+__global__ void __launch_bounds__(FH_THREADS, 1) forward_h_kernel(FwdHArgs a) {
   constexpr int NT = 16 * L;
   constexpr int IMG_BYTES = NT * 128;                // one (hi | lo) B image: NT rows x 64 fp16
   constexpr int STAGE_BYTES = 2 * IMG_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * NT <= 64 ? 64 : 2 * NT <= 128 ? 128 : 2 * NT <= 256 ? 256 : 512;
+  constexpr int NSTAGE_WARPS = 9;                    // everyone but the loader stages the A tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_t = smem;
@@ -373,6 +408,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) forward_h_kernel(FwdHArgs a) {
   uint64_t* b_full = bars, *b_empty = bars + FT_STAGES, *acc_full = bars + 2 * FT_STAGES, *acc_empty = bars + 2 * FT_STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FT_STAGES + 4);
   int* rexp = reinterpret_cast<int*>(bars + 2 * FT_STAGES + 6);      // [128] row exponents
+  float* xch = reinterpret_cast<float*>(rexp + FT_TM);               // [128][L] partial logits of the second column half
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Ds = a.Ds;
   const int64_t t0 = (int64_t)blockIdx.x * FT_TM;
@@ -382,43 +418,57 @@ __global__ void __launch_bounds__(FT_THREADS, 1) forward_h_kernel(FwdHArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < FT_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
     fence_barrier_init();
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
-
-  // ---- A tile: one image row per warp iteration (lane = 4 consecutive k), row maximum by shuffle, scaled fp16 hi/lo
-  for (int t = warp; t < FT_TM; t += FT_THREADS / 32) {
-    const int64_t tg = t0 + t;
-    const int k = 4 * lane;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tg < a.B && k < Ds) v = __ldg(reinterpret_cast<const float4*>(a.e_near + tg * Ds + k));
-    float mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const int ex = (mx > 0.f && mx < 3.0e38f) ? exponent_of(mx) - FH_TROW : 0;
-    if (lane == 0) rexp[t] = ex;
-    if (k < nchunks * FH_KCH) {
-      const float x0 = scale_pow2(v.x, -ex), x1 = scale_pow2(v.y, -ex), x2 = scale_pow2(v.z, -ex), x3 = scale_pow2(v.w, -ex);
-      const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
-      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-      const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
-      const uint32_t off = (uint32_t)((k >> 6) * 16384) + k128_chunk_off(t, (k & 63) >> 3) + (uint32_t)((lane & 1) * 8);
-      uint2 hv, lv;
-      hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-      lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-      *reinterpret_cast<uint2*>(a_t + off) = hv;
-      *reinterpret_cast<uint2*>(a_t + 2 * 16384 + off) = lv;
-    }
-  }
-  fence_async_proxy();
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();               // barriers initialised, TMEM allocated: the B loader may start right away
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 5) {
+  // ---- A tile (warps 0-8; warp 9 is already streaming B images): one image row per (warp, iteration), lane = 4
+  //      consecutive k; all global loads are issued before the first use, row maximum by shuffle, scaled fp16 hi/lo
+  if (warp < NSTAGE_WARPS) {
+    constexpr int ROWS_PER_WARP = (FT_TM + NSTAGE_WARPS - 1) / NSTAGE_WARPS;
+    const int k = 4 * lane;
+    float4 v[ROWS_PER_WARP];
+#pragma unroll
+    for (int u = 0; u < ROWS_PER_WARP; ++u) {
+      const int t = warp + NSTAGE_WARPS * u;
+      const int64_t tg = t0 + t;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < FT_TM && tg < a.B && k < Ds) v[u] = __ldg(reinterpret_cast<const float4*>(a.e_near + tg * Ds + k));
+    }
+#pragma unroll
+    for (int u = 0; u < ROWS_PER_WARP; ++u) {
+      const int t = warp + NSTAGE_WARPS * u;
+      if (t >= FT_TM) continue;       // warp-uniform
+      float mx = fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const int ex = (mx > 0.f && mx < 3.0e38f) ? exponent_of(mx) - FH_TROW : 0;
+      if (lane == 0) rexp[t] = ex;
+      if (k < nchunks * FH_KCH) {
+        const float x0 = scale_pow2(v[u].x, -ex), x1 = scale_pow2(v[u].y, -ex), x2 = scale_pow2(v[u].z, -ex), x3 = scale_pow2(v[u].w, -ex);
+        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+        const uint32_t off = (uint32_t)((k >> 6) * 16384) + k128_chunk_off(t, (k & 63) >> 3) + (uint32_t)((lane & 1) * 8);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(a_t + off) = hv;
+        *reinterpret_cast<uint2*>(a_t + 2 * 16384 + off) = lv;
+      }
+    }
+    fence_async_proxy();
+    // the MMA issuer waits for all staging warps on a named barrier (the loader does not take part)
+    asm volatile("bar.sync 1, %0;" ::"n"(NSTAGE_WARPS * 32) : "memory");
+  }
+
+  if (warp == 9) {
     if (lane == 0) {
       int it = 0;
       for (int j = 0; j < ntiles; ++j) {
@@ -430,7 +480,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) forward_h_kernel(FwdHArgs a) {
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     if (lane == 0) {
       // kind::f16, fp16 x fp16 -> fp32, both K-major, N = NT, M = 128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(FT_TM >> 4) << 24);
@@ -460,7 +510,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) forward_h_kernel(FwdHArgs a) {
       }
     }
   } else {
-    const int row = warp * 32 + lane;
+    // ===== epilogue: warp = (column half, TMEM lane quadrant); one image row per thread, half of the tile's columns.
+    //       One warp per scheduler was latency bound (2400 cycles per tile against 1920 of MMAs); two halve it.
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
     const int64_t tg = t0 + row;
     const bool live = tg < a.B;
     float pp[4] = {0.f, 0.f, 0.f, 0.f};
@@ -472,32 +525,38 @@ __global__ void __launch_bounds__(FT_THREADS, 1) forward_h_kernel(FwdHArgs a) {
     float facc[L];
 #pragma unroll
     for (int l = 0; l < L; ++l) facc[l] = 0.f;
+    // far-environment entries of my row, fetched two tiles ahead: the load latency (~1 us) must not sit between the
+    // accumulator becoming ready and its drain
+    auto load_e = [&](int j) {
+      float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live && j < ntiles && 4 * j < Ds) e = __ldg(reinterpret_cast<const float4*>(a.e_far + tg * Ds + 4 * j));
+      return e;
+    };
+    float4 e_cur = load_e(0), e_nxt = load_e(1);
     for (int j = 0; j < ntiles; ++j) {
       const int b = j & 1;
-      float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live && 4 * j < Ds) e4 = __ldg(reinterpret_cast<const float4*>(a.e_far + tg * Ds + 4 * j));
-      const float ek[4] = {e4.x, e4.y, e4.z, e4.w};
+      const float4 e_nn = load_e(j + 2);
+      const float ek[4] = {e_cur.x, e_cur.y, e_cur.z, e_cur.w};
+      e_cur = e_nxt; e_nxt = e_nn;
       mbar_wait(&acc_full[b], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-#pragma unroll
-      for (int cb = 0; cb < NT / 32; ++cb) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * NT + cb * 32), v);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int col = cb * 32 + e;                       // compile-time: (k_local; l, m, n)
-          const int kl = col / (4 * L), r = col % (4 * L), l = r >> 2, mn = r & 3;
-          facc[l] = fmaf(v[e], pp[mn] * ek[kl], facc[l]);
-        }
-      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * NT);
+      if (half == 0) fh_epilogue_tile<L, 0>(taddr, pp, ek, facc);
+      else fh_epilogue_tile<L, 1>(taddr, pp, ek, facc);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[b]);
     }
-    if (live) {
-      const int ex = rexp[row] + bond_exponent(a.maxbits);       // undo both scalings (exact powers of two)
+    // combine the two column halves, undo both scalings (exact powers of two)
+    if (half == 1) {
 #pragma unroll
-      for (int l = 0; l < L; ++l) a.f[tg * L + l] = scale_pow2(facc[l], ex);
+      for (int l = 0; l < L; ++l) xch[row * L + l] = facc[l];
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    if (half == 0 && live) {
+      const int ex = rexp[row] + bond_exponent(a.maxbits);
+#pragma unroll
+      for (int l = 0; l < L; ++l) a.f[tg * L + l] = scale_pow2(facc[l] + xch[row * L + l], ex);
     }
   }
   tc_fence_before();
@@ -506,7 +565,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) forward_h_kernel(FwdHArgs a) {
 }
 
 template <int L>
-size_t forward_h_smem() { return (size_t)FH_A_BYTES + (size_t)FT_STAGES * 2 * 16 * L * 128 + 1024 + 1024; }
+size_t forward_h_smem() { return (size_t)FH_A_BYTES + (size_t)FT_STAGES * 2 * 16 * L * 128 + 1024 + (size_t)FT_TM * L * 4 + 1024; }
 
 template <int L>
 size_t forward_tc_smem() { return (size_t)2 * FT_A_BYTES + (size_t)FT_STAGES * 2 * 16 * 16 * L * 4 + 256 + 1024; }
@@ -548,7 +607,7 @@ int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_
       TRMPS_CUDA_OK(cudaFuncSetAttribute(forward_h_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
       attr_h = true;
     }
-    forward_h_kernel<10><<<(unsigned)ceil_div64(B, FT_TM), FT_THREADS, smem_h, st>>>(h);
+    forward_h_kernel<10><<<(unsigned)ceil_div64(B, FT_TM), FH_THREADS, smem_h, st>>>(h);
     TRMPS_LAUNCH_OK("forward_h_kernel");
     return TRMPS_OK;
   }

@@ -167,5 +167,6 @@ int main() {
   for (int kind : {0, 1}) for (int N : {64, 128}) for (int na : {2, 4}) if (run(N, 256, kind, false, na)) return 1;
   for (int kind : {0, 1}) if (run(256, 256, kind, false, 2)) return 1;
   for (int N : {128, 256}) if (run(N, 256, 0, false, 1, 1)) return 1;
+  for (int N : {144, 160, 176, 192, 208, 224, 240}) if (run(N, 256, 0, false)) return 1;
   return 0;
 }
