@@ -348,7 +348,10 @@ def run_ours(args, rank, local_rank, world):
     roofline_fwd = dict(kernel="forward_h_kernel, tcgen05 kind::f16 with fp16 hi/lo operands (f(bond) and f(delta): 2 of the 3 dense "
                                "contractions per update; achieved counts algorithmic FP32 flops, the tensor pipe executes 3x as "
                                "many 16-bit flops; time includes the absmax and image-prep kernels)",
-                        bound="tensor", achieved=achieved, peak=fp16_peak, unit="TFLOP/s", frac=achieved / fp16_peak, traffic=None,
+                        bound="tensor", achieved=achieved, peak=fp16_peak, unit="TFLOP/s", frac=achieved / fp16_peak,
+                        traffic=61.7e6 if (B == 60000 and D == 120) else None,
+                        traffic_source="ncu --set full, dram__bytes_read+write per launch at B=60000, D=120 (profiles/r1g_tensor_kernels_ncu.txt): "
+                                       "the two environment reads, no re-reads",
                         pipe_frac=3.0 * achieved / fp16_peak,
                         peak_source="%s bf16 sustained (16-bit dense tensor peak)" % peaks["source"], avg_launch_ms=fwd_ms / max(fwd_n, 1),
                         launches=fwd_n, share_of_step=fwd_ms / ms_total)
@@ -367,7 +370,8 @@ def run_ours(args, rank, local_rank, world):
                                "rotation recurrences: ~21k cycles per round), not by bandwidth or flops" %
                                (svd_n, total_sweeps / max(1.0, float(svd_n)), rounds_per_sweep),
                         bound="hbm", achieved=svd_gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=svd_gbs / peaks["hbm_gbs"],
-                        traffic=None, peak_source="%s HBM copy bandwidth" % peaks["source"],
+                        traffic=None, traffic_source="ncu cannot replay the cooperative cluster kernel (LaunchFailed); the working set (2.9 MB) is L2 resident",
+                        peak_source="%s HBM copy bandwidth" % peaks["source"],
                         avg_launch_ms=svd_ms / max(1.0, float(svd_n)), share_of_step=svd_ms / ms_total,
                         note="algorithmic bytes = row-exchange traffic through L2; DRAM traffic is the 2.9 MB bond once")
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
