@@ -512,3 +512,38 @@ def test_other_label_counts(L, D):
     assert abs(sc[0] - tr[0]["cost0"]) < 1e-4 * abs(tr[0]["cost0"])
     sv = np.sort(st.singular_values().cpu().numpy())[::-1][:tr[0]["m"]]
     assert rel(sv, tr[0]["s"][:tr[0]["m"]]) < 1e-4
+
+
+@pytest.mark.parametrize("direction", [+1, -1])
+def test_bond_step_with_hessian_matches_oracle(direction):
+    """use_hessian=True (optimizer.py:229-237, baseoptimizer.py:32-35): delta = gradient / (sum_t h(1-h) C^2 + 2 reg)."""
+    N, B, L, loc = 8, 400, 10, 4
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=43, loc=loc)
+    st = make_state(N, B, L, 24, nodes, loc, phi, lab)
+    st.init_env(loc)
+    lr = 0.05
+    p = o.SweepParams(max_size=24, use_hessian=True)
+    C1s, C2s = o.setup_environments(nodes, loc, phi, L)
+    tr = o.Trace()
+    if direction > 0:
+        a_j, n1 = o.update_right(loc, nodes[loc], list(nodes), C1s, C2s, phi, lab, lr, p, tr)
+    else:
+        C2s[loc] = o.chain_left(C2s[loc + 1], phi[loc + 1], nodes[loc + 1])
+        lib = nat.load()
+        nat.check(lib.trmps_env_step(st.feat[loc + 1].data_ptr(), nat.FM_PRECOMPUTED, B, st.Ds, -1,
+                                     st.envR[loc + 1].data_ptr(), st.slots[loc + 1].data_ptr(),
+                                     st.dims[loc + 2:].data_ptr(), st.envR[loc].data_ptr(), None), "env_step")
+        a_j, n1 = o.update_left(loc, nodes[loc], list(nodes), C1s, C2s, phi, lab, lr, p, tr)
+    st.bond_step(loc, direction, dev.make_opt(lr=lr, max_size=24, use_hessian=True))
+    torch.cuda.synchronize()
+    iw, sc = st.iwork.cpu().numpy(), st.scalars().cpu().numpy()
+    last = tr[-1]
+    assert int(iw[nat.I_ACCEPT]) == int(last['accepted'])
+    assert int(iw[nat.I_TRIALS]) == last['trials']
+    assert abs(sc[nat.S_COST0] - last['cost0']) < 1e-5 * abs(last['cost0'])
+    assert abs(sc[nat.S_COST1] - last['cost1']) < 1e-5 * abs(last['cost1'])
+    assert abs(sc[nat.S_GDC] - last['gdc']) < 1e-4 * abs(last['gdc'])
+    assert int(iw[nat.I_M]) == last['m']
+    sv = st.singular_values().cpu().numpy()[:len(last['s'])]
+    big = last['s'] > 1e-3 * last['s'][0]
+    assert np.max(np.abs(sv[big] - last['s'][big]) / last['s'][big]) < RTOL
