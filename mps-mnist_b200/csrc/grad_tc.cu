@@ -20,7 +20,8 @@ namespace trmps {
 
 namespace {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 288;             // warps 0-7 form the operand tiles (and drain TMEM at the end), warp 8 issues the MMAs
+constexpr int TC_FORMERS = 256;
 constexpr int TC_KCH = 16;                 // images per stage (two K=8 MMA steps)
 constexpr int TC_STAGES = 3;
 constexpr int TC_TM = 256, TC_TN = 256;    // CTA output tile
@@ -41,8 +42,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) { }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {      // sleeps in hardware (suspend-time hint)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -125,8 +136,9 @@ __device__ __forceinline__ uint32_t tile_off(int mn, int k, int atoms_per_k) {
 __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);   // empty[TC_STAGES], done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TC_STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);   // empty[TC_STAGES], done, full[TC_STAGES]
+  uint64_t* full = bars + TC_STAGES + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Ds = g.Ds, L2 = 2 * g.L;
   const int c0 = blockIdx.x * TC_TN, a0 = blockIdx.y * TC_TM;
@@ -137,6 +149,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
 
   if (tid == 0) {
     for (int s = 0; s <= TC_STAGES; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < TC_STAGES; ++s) mbar_init(&full[s], TC_FORMERS);
     fence_barrier_init();
   }
   __syncwarp();
@@ -213,35 +226,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
     tick(2);
     fence_async_proxy();          // make the generic-proxy stores visible to the tensor core (async proxy)
     tick(3);
-    __syncthreads();
+    mbar_arrive(&full[s]);        // no block barrier: the issuer warp waits for all 256 producers on the stage's mbarrier
     tick(4);
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t acc0 = ch > 0 ? 1u : 0u;
+  };
+  // MMAs of one chunk (issuer thread)
+  auto issue_chunk = [&](int ch) {
+    const int s = ch % TC_STAGES, it = ch / TC_STAGES;
+    uint8_t* st = smem + s * TC_STAGE_BYTES;
+    uint8_t* a_hi = st, *a_lo = st + TC_A_BYTES, *b_hi = st + 2 * TC_A_BYTES, *b_lo = st + 2 * TC_A_BYTES + TC_B_BYTES;
+    mbar_wait(&full[s], (uint32_t)(it & 1));
+    tc_fence_after();
+    const uint32_t acc0 = ch > 0 ? 1u : 0u;
 #pragma unroll
-      for (int kb = 0; kb < TC_KCH / 8; ++kb) {
-        const uint32_t koffA = 2 * kb * (TC_TM / 32) * TC_ATOM, koffB = 2 * kb * (TC_TN / 32) * TC_ATOM;   // two 4-k groups per MMA
-        const uint64_t dbh = make_desc_mn_sw128(smem_u32(b_hi) + koffB, TC_ATOM, (TC_TN / 32) * TC_ATOM);
-        const uint64_t dbl = make_desc_mn_sw128(smem_u32(b_lo) + koffB, TC_ATOM, (TC_TN / 32) * TC_ATOM);
+    for (int kb = 0; kb < TC_KCH / 8; ++kb) {
+      const uint32_t koffA = 2 * kb * (TC_TM / 32) * TC_ATOM, koffB = 2 * kb * (TC_TN / 32) * TC_ATOM;   // two 4-k groups per MMA
+      const uint64_t dbh = make_desc_mn_sw128(smem_u32(b_hi) + koffB, TC_ATOM, (TC_TN / 32) * TC_ATOM);
+      const uint64_t dbl = make_desc_mn_sw128(smem_u32(b_lo) + koffB, TC_ATOM, (TC_TN / 32) * TC_ATOM);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const uint32_t moff = mt * 4 * TC_ATOM;      // rows 128.. of the A tile: MN blocks 4..7
-          const uint64_t dah = make_desc_mn_sw128(smem_u32(a_hi) + koffA + moff, TC_ATOM, (TC_TM / 32) * TC_ATOM);
-          const uint64_t dal = make_desc_mn_sw128(smem_u32(a_lo) + koffA + moff, TC_ATOM, (TC_TM / 32) * TC_ATOM);
-          const uint32_t d = tmem_base + mt * TC_TN;
-          const uint32_t acc = (kb > 0) ? 1u : acc0;
-          umma_tf32(d, dah, dbh, idesc, acc);
-          umma_tf32(d, dal, dbh, idesc, 1u);
-          umma_tf32(d, dah, dbl, idesc, 1u);
-        }
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint32_t moff = mt * 4 * TC_ATOM;      // rows 128.. of the A tile: MN blocks 4..7
+        const uint64_t dah = make_desc_mn_sw128(smem_u32(a_hi) + koffA + moff, TC_ATOM, (TC_TM / 32) * TC_ATOM);
+        const uint64_t dal = make_desc_mn_sw128(smem_u32(a_lo) + koffA + moff, TC_ATOM, (TC_TM / 32) * TC_ATOM);
+        const uint32_t d = tmem_base + mt * TC_TN;
+        const uint32_t acc = (kb > 0) ? 1u : acc0;
+        umma_tf32(d, dah, dbh, idesc, acc);
+        umma_tf32(d, dal, dbh, idesc, 1u);
+        umma_tf32(d, dah, dbl, idesc, 1u);
       }
-      umma_commit(&bars[s]);                          // stage s may be overwritten once these MMAs have read it
-      if (ch == nch - 1) umma_commit(&bars[TC_STAGES]);
     }
+    umma_commit(&bars[s]);                          // stage s may be overwritten once these MMAs have read it
+    if (ch == nch - 1) umma_commit(&bars[TC_STAGES]);
   };
 
-  // software pipeline: the global loads of chunks ch+1 and ch+2 are in flight while chunk ch is converted and issued
-  {
+  // software pipeline: the global loads of chunks ch+1 and ch+2 are in flight while chunk ch is converted and stored
+  if (tid < TC_FORMERS) {
     float4 ra0[4], rb0[4], ra1[4], rb1[4];
     float pa0[4], pb0[4], pa1[4], pb1[4];
     if (nch > 0) load_chunk(0, ra0, rb0, pa0, pb0);
@@ -254,6 +272,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
         if (ch + 3 < nch) load_chunk(ch + 3, ra1, rb1, pa1, pb1);
       }
     }
+  } else if (tid == TC_FORMERS) {
+    for (int ch = 0; ch < nch; ++ch) issue_chunk(ch);
   }
 
   if (timer) for (int k = 0; k < 6; ++k) g.dbg[k] = (float)tacc[k];
@@ -261,7 +281,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
   float* out = g.gpart + (size_t)blockIdx.z * g.R * g.Cc;
   const int mt = warp >> 2, quad = warp & 3;
   const int row = a0 + mt * 128 + quad * 32 + lane;
-  if (nch > 0) {
+  if (warp >= 8) {
+    // the issuer warp has nothing to drain
+  } else if (nch > 0) {
     mbar_wait(&bars[TC_STAGES], 0);
     tc_fence_after();
 #pragma unroll 1
