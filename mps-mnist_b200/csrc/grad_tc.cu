@@ -6,7 +6,7 @@
 // a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (dropped term ~2^-22), because plain TF32 (10-bit mantissa) misses
 // the 1e-4 tolerance on this cancellation-heavy sum.
 //
-// Neither operand exists in memory: both are rank-1-per-image products.  All 256 threads of the CTA form the
+// Neither operand exists in memory: both are rank-1-per-image products.  512 producer threads of the CTA form the
 // hi/lo tiles while staging global -> registers -> shared memory, directly in the MN-major 128-byte-swizzled
 // canonical layout the MMA reads (both operands are "transposed": the contraction index t is the slow one in
 // memory; for TF32 tcgen05 supports that only with the SWIZZLE_128B_BASE32B layout -- verified with
@@ -20,10 +20,11 @@ namespace trmps {
 
 namespace {
 
-constexpr int TC_THREADS = 288;             // warps 0-7 form the operand tiles (and drain TMEM at the end), warp 8 issues the MMAs
-constexpr int TC_FORMERS = 256;
+constexpr int TC_FORMERS = 512;             // warps 0-15 form the operand tiles (warps 0-7 also drain TMEM at the end)
+constexpr int TC_THREADS = TC_FORMERS + 32;  // + one warp that issues the MMAs
 constexpr int TC_KCH = 16;                 // images per stage (two K=8 MMA steps)
 constexpr int TC_STAGES = 3;
+constexpr int TC_RPT = TC_KCH * 64 / TC_FORMERS;     // image rows of a chunk per producer thread
 constexpr int TC_TM = 256, TC_TN = 256;    // CTA output tile
 constexpr int TC_ATOM = 512;               // one swizzle atom: 4 k-rows x 128 B (32 MN elements), 32-byte units XORed with the row
 constexpr int TC_A_BYTES = (TC_TM / 32) * (TC_KCH / 4) * TC_ATOM;   // 16 KB (hi) per stage
@@ -159,7 +160,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // this thread stages one quad of A rows and one quad of B columns for image rows ksub + 4 r, r = 0..3
+  // this thread stages one quad of A rows and one quad of B columns for image rows ksub + KS r, r = 0..TC_RPT-1
+  constexpr int KS = TC_FORMERS / 64;
   const int q4 = tid & 63, ksub = tid >> 6;
   const int arow = a0 + 4 * q4, ccol = c0 + 4 * q4;
   const bool va = arow < g.R, vc = ccol < g.Cc;
@@ -173,10 +175,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
 
   // global -> registers for one chunk: RAW rows of e_near / e_far plus their per-image scale factors for image rows
   // ksub + 4 r.  Nothing here consumes a loaded value, so all 16 loads of a chunk stay in flight.
-  auto load_chunk = [&](int ch, float4 (&ra)[4], float4 (&rb)[4], float (&pa)[4], float (&pb)[4]) {
+  auto load_chunk = [&](int ch, float4 (&ra)[TC_RPT], float4 (&rb)[TC_RPT], float (&pa)[TC_RPT], float (&pb)[TC_RPT]) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int64_t t = tbeg + (int64_t)ch * TC_KCH + ksub + 4 * r;
+    for (int r = 0; r < TC_RPT; ++r) {
+      const int64_t t = tbeg + (int64_t)ch * TC_KCH + ksub + KS * r;
       ra[r] = make_float4(0.f, 0.f, 0.f, 0.f);
       rb[r] = ra[r];
       pa[r] = 0.f;
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
     }
   };
   // registers -> tf32 hi/lo tiles in stage ch % TC_STAGES, then one thread issues the MMAs of the chunk
-  auto process_chunk = [&](int ch, const float4 (&ra)[4], const float4 (&rb)[4], const float (&pa)[4], const float (&pb)[4]) {
+  auto process_chunk = [&](int ch, const float4 (&ra)[TC_RPT], const float4 (&rb)[TC_RPT], const float (&pa)[TC_RPT], const float (&pb)[TC_RPT]) {
     const int s = ch % TC_STAGES, it = ch / TC_STAGES;
     uint8_t* st = smem + s * TC_STAGE_BYTES;
     uint8_t* a_hi = st, *a_lo = st + TC_A_BYTES, *b_hi = st + 2 * TC_A_BYTES, *b_lo = st + 2 * TC_A_BYTES + TC_B_BYTES;
@@ -202,8 +204,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
     if (ch >= TC_STAGES) mbar_wait(&bars[s], (uint32_t)((it - 1) & 1));   // MMAs that read this stage are done
     tick(1);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int k = ksub + 4 * r;
+    for (int r = 0; r < TC_RPT; ++r) {
+      const int k = ksub + KS * r;
       {
         float4 hi, lo;
         const float vx = ra[r].x * pa[r], vy = ra[r].y * pa[r], vz = ra[r].z * pa[r], vw = ra[r].w * pa[r];
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
     tick(2);
     fence_async_proxy();          // make the generic-proxy stores visible to the tensor core (async proxy)
     tick(3);
-    mbar_arrive(&full[s]);        // no block barrier: the issuer warp waits for all 256 producers on the stage's mbarrier
+    mbar_arrive(&full[s]);        // no block barrier: the issuer warp waits for all producers on the stage's mbarrier
     tick(4);
   };
   // MMAs of one chunk (issuer thread)
@@ -260,8 +262,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
 
   // software pipeline: the global loads of chunks ch+1 and ch+2 are in flight while chunk ch is converted and stored
   if (tid < TC_FORMERS) {
-    float4 ra0[4], rb0[4], ra1[4], rb1[4];
-    float pa0[4], pb0[4], pa1[4], pb1[4];
+    float4 ra0[TC_RPT], rb0[TC_RPT], ra1[TC_RPT], rb1[TC_RPT];
+    float pa0[TC_RPT], pb0[TC_RPT], pa1[TC_RPT], pb1[TC_RPT];
     if (nch > 0) load_chunk(0, ra0, rb0, pa0, pb0);
     if (nch > 1) load_chunk(1, ra1, rb1, pa1, pb1);
     for (int ch = 0; ch < nch; ch += 2) {
