@@ -165,6 +165,9 @@ int launch_sum_parts(const float* part, int nparts, int64_t n, float* out, cudaS
 int launch_grad_tc(const float* e_near, const float* e_far, const float* phi_near, const float* sres, float* gpart, int gsplit,
                    int64_t B, int Ds, int L, cudaStream_t st, float* dbg = nullptr);
 int grad_tc_splits(int64_t B, int Ds, int L, int sms);
+bool grad_h_supported(int64_t B, int Ds, int L);
+int launch_grad_h(const float* e_near, const float* e_far, const float* phi_near, const float* sres, float* gpart, int gsplit,
+                  int64_t B, int Ds, int L, int32_t* scratch, float* out, cudaStream_t st);
 bool chain_tc_supported(int Ds);
 int chain_tc_debug(float* out64);
 int64_t chain_tc_image_floats(int Ds, int nsteps);

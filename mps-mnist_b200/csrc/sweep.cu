@@ -231,7 +231,13 @@ static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const Bond
   }
   {
     ProfScope ps(PROF_GRAD, st);
-    if (g_grad_impl == 0) {
+    if (g_grad_impl == 2 && grad_h_supported(s->B, Ds, L)) {
+      // fp16 hi/lo operands (option 2; parity-green but not yet faster than 3xTF32: its producers' global loads are
+      // single-buffered); the per-image exponents live in the (still unused) delta buffer
+      if ((rc = launch_grad_h(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit_tc, s->B, Ds, L,
+                              reinterpret_cast<int32_t*>(w + lay.deltaM), w + lay.gradM, st)))
+        return rc;
+    } else if (g_grad_impl != 1) {
       if ((rc = launch_grad_tc(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit_tc, s->B, Ds, L, st, getenv("TRMPS_GRAD_DEBUG") ? w + lay.hres : nullptr))) return rc;
       if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit_tc, RC, w + lay.gradM, st))) return rc;
     } else {
@@ -381,7 +387,7 @@ extern "C" int trmps_abi_version(void) { return TRMPS_ABI_VERSION; }
 extern "C" int64_t trmps_launch_count(void) { return (int64_t)g_launches; }
 
 extern "C" int trmps_set_option(int32_t option, int32_t value) {
-  if (option == 0 && (value == 0 || value == 1)) { g_grad_impl = value; return TRMPS_OK; }
+  if (option == 0 && (value == 0 || value == 1 || value == 2)) { g_grad_impl = value; return TRMPS_OK; }
   if (option == 1 && (value == 0 || value == 1 || value == 2)) { g_fwd_impl = value; return TRMPS_OK; }
   if (option == 2 && (value == 0 || value == 1)) { g_chain_impl = value; return TRMPS_OK; }
   set_error("trmps_set_option: unknown option %d / value %d", option, value);

@@ -363,6 +363,11 @@ def test_tcgen05_gradient_matches_simt_and_fp64(D, B):
         st.bond_gradient(loc, +1, opt)
         torch.cuda.synchronize()
         g_simt = st.grad_matrix().clone().cpu().numpy()
+        nat.set_option(nat.OPT_GRAD_IMPL, nat.GRAD_TCGEN05_F16)
+        st.grad_matrix().zero_()
+        st.bond_gradient(loc, +1, opt)
+        torch.cuda.synchronize()
+        g_f16 = st.grad_matrix().clone().cpu().numpy()
         nat.set_option(nat.OPT_GRAD_IMPL, nat.GRAD_TCGEN05)
         st.grad_matrix().zero_()
         st.bond_gradient(loc, +1, opt)
@@ -380,6 +385,7 @@ def test_tcgen05_gradient_matches_simt_and_fp64(D, B):
     assert rel(got_simt, G64) < 1e-5
     assert rel(got_tc, G64) < 1e-5                      # 3xTF32 keeps FP32-level accuracy (tolerance is 1e-4)
     assert rel(g_tc, g_simt) < 1e-5
+    assert rel(g_f16, g_simt) < 1e-5                    # fp16 hi/lo variant (option 2)
     pad = g_tc.copy().reshape(2, st.Ds, L, 2, st.Ds)
     pad[:, :dn, :, :, :df] = 0
     assert np.all(pad == 0)
