@@ -432,7 +432,6 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
     // running pointer to my feature of the site two steps ahead (one 64-bit add per step instead of a multiply)
     const int64_t feat_stride = feat_site_offset(a.fm, a.B, 1) * a.dir;
     const float* feat_ptr = a.feat + feat_site_offset(a.fm, a.B, a.first) + (a.fm == TRMPS_FM_PRECOMPUTED ? 2 : 1) * t;
-    int feat_step = 0;
     auto load_raw = [&](int step) -> float2 {          // called with step = 0, 1, 2, ... in order
       float2 r = make_float2(0.f, 0.f);
       if (live && step < nsteps) {
@@ -440,7 +439,6 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
         else r.x = __ldg(feat_ptr);
       }
       feat_ptr += feat_stride;
-      ++feat_step;
       return r;
     };
     auto phi_of_raw = [&](float2 raw) -> float2 {

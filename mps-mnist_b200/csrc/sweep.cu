@@ -212,6 +212,7 @@ static float cost_norm(const trmps_sweep* s) {
 // loss + gradient (+Hessian) + all-reduce + finish; leaves G in gradM, delta in deltaM (Hessian) or gradM
 static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, int from_parts,
                        cudaStream_t st) {
+  static const bool grad_debug = getenv("TRMPS_GRAD_DEBUG") != nullptr;      // development: phase timers of grad_tc in hres
   const int Ds = s->Ds, L = s->L;
   const int64_t RC = (int64_t)2 * Ds * 2 * L * Ds;
   float* w = s->work;
@@ -238,7 +239,7 @@ static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const Bond
                               reinterpret_cast<int32_t*>(w + lay.deltaM), w + lay.gradM, st)))
         return rc;
     } else if (g_grad_impl != 1) {
-      if ((rc = launch_grad_tc(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit_tc, s->B, Ds, L, st, getenv("TRMPS_GRAD_DEBUG") ? w + lay.hres : nullptr))) return rc;
+      if ((rc = launch_grad_tc(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit_tc, s->B, Ds, L, st, grad_debug ? w + lay.hres : nullptr))) return rc;
       if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit_tc, RC, w + lay.gradM, st))) return rc;
     } else {
       if ((rc = launch_grad(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit, s->B, Ds, L, false, st))) return rc;
