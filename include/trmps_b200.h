@@ -92,7 +92,8 @@ typedef struct {
   int32_t updates_per_step;   /*                                            baseoptimizer.py:324-332 */
   int32_t use_hessian;        /* diagonal Hessian scaling                   optimizer.py:229-237 */
   int32_t max_svd_sweeps;     /* 0 = default (30) */
-  int32_t reserved;
+  int32_t single_site;        /* 1: single-site DMRG updates (singlesiteOptimizer.py:49-138): trmps_bond_step(site, dir)
+                                 optimises the special node at `site` alone, splits it and lets node site+dir absorb S V */
 } trmps_opt;
 
 /* offsets (in floats) of the library-defined regions inside the caller's `work` buffer */

@@ -182,7 +182,12 @@ int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_
 int forward_rq(int Ds, int L);
 int svd_block_rows(int R, int Cc);
 
-int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, cudaStream_t st);
+// special_out: where the S V part goes (the special node, or a scratch buffer for the single-site move);
+// single: the bond has a unit far site (columns with n = 1 are zero): at most L * d_far singular values are non-zero
+int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, cudaStream_t st,
+              float* special_out = nullptr, bool single = false);
+int launch_special_to_bond(const float* special, float* M, float* phi_far, int Ds, int L, int64_t B, int dir, cudaStream_t st);
+int launch_site_absorb(const float* tmp, const float* node, float* special, int Ds, int L, int dir, cudaStream_t st);
 int allreduce_sum(void* comm, float* buf, int64_t count, cudaStream_t st);
 
 }  // namespace trmps

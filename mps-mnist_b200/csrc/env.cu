@@ -222,24 +222,61 @@ __global__ void special_to_matrix_kernel(const float* __restrict__ sp, float* __
   M[((int64_t)(m * Ds + i)) * ((int64_t)L * Ds) + (int64_t)l * Ds + k] = sp[idx];
 }
 
-// Inference as a bond with a unit far site: M[(m,i)][(l,n,k)] = special[l][m][i][k] for n = 0, zero for n = 1, and
-// phi_far = (1, 0) for every image.  This is the layout the tensor-core forward contraction consumes.
+// A special node as a bond with a unit far site: M[(m,a)][(l,n,b)] = special[l][m][a][b] for n = 0 (dir > 0; for
+// dir < 0 the roles of the two bond indices swap: rows (m,b), columns (l,0,a)), zero for n = 1, and
+// phi_far = (1, 0) for every image.  This is the layout the two-site contraction kernels consume; it serves the
+// special-node contraction of predict (mps.py:552-557) and the single-site optimizer (singlesiteOptimizer.py:49-138).
 __global__ void special_to_bond_kernel(const float* __restrict__ sp, float* __restrict__ M, float2* __restrict__ phi_far,
-                                       int Ds, int L, int64_t B) {
+                                       int Ds, int L, int64_t B, int dir) {
   const int64_t total = (int64_t)L * 2 * Ds * Ds;
   const int64_t Cc = (int64_t)2 * L * Ds;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(idx % Ds);
+    const int b = (int)(idx % Ds);
     int64_t r = idx / Ds;
-    const int i = (int)(r % Ds);
+    const int a = (int)(r % Ds);
     r /= Ds;
     const int m = (int)(r % 2), l = (int)(r / 2);
+    const int i = dir > 0 ? a : b, k = dir > 0 ? b : a;          // i: near bond (row), k: far bond (column)
     float* row = M + (int64_t)(m * Ds + i) * Cc + (int64_t)(l * 2) * Ds;
     row[k] = sp[idx];
     row[Ds + k] = 0.f;
   }
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < B; t += (int64_t)gridDim.x * blockDim.x)
     phi_far[t] = make_float2(1.f, 0.f);
+}
+
+int launch_special_to_bond(const float* special, float* M, float* phi_far, int Ds, int L, int64_t B, int dir, cudaStream_t st) {
+  special_to_bond_kernel<<<296, 256, 0, st>>>(special, M, reinterpret_cast<float2*>(phi_far), Ds, L, B, dir);
+  TRMPS_LAUNCH_OK("special_to_bond_kernel");
+  return TRMPS_OK;
+}
+
+// Single-site move: the S V part of the split (tmp, special layout with n = 0: right move tmp[l][0][q][k], left move
+// tmp[l][0][k][q]) is absorbed by the neighbouring node (singlesiteOptimizer.py:124-125 / :76-77):
+//   right: special[l][n][q][k'] = sum_k tmp[l][0][q][k] node[n][k][k']     left: special[l][n][k'][q] = sum_k node[n][k'][k] tmp[l][0][k][q]
+__global__ void site_absorb_kernel(const float* __restrict__ tmp, const float* __restrict__ node, float* __restrict__ special,
+                                   int Ds, int L, int dir) {
+  const int64_t total = (int64_t)L * 2 * Ds * Ds;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int y = (int)(idx % Ds), x = (int)((idx / Ds) % Ds);
+    const int n = (int)((idx / ((int64_t)Ds * Ds)) % 2), l = (int)(idx / ((int64_t)2 * Ds * Ds));
+    const float* t0 = tmp + (int64_t)(l * 2) * Ds * Ds;
+    const float* nd = node + (int64_t)n * Ds * Ds;
+    float acc = 0.f;
+    if (dir > 0) {
+      for (int k = 0; k < Ds; ++k) acc = fmaf(t0[(int64_t)x * Ds + k], nd[(int64_t)k * Ds + y], acc);
+    } else {
+      for (int k = 0; k < Ds; ++k) acc = fmaf(nd[(int64_t)x * Ds + k], t0[(int64_t)k * Ds + y], acc);
+    }
+    special[idx] = acc;
+  }
+}
+
+int launch_site_absorb(const float* tmp, const float* node, float* special, int Ds, int L, int dir, cudaStream_t st) {
+  const int64_t total = (int64_t)L * 2 * Ds * Ds;
+  site_absorb_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(tmp, node, special, Ds, L, dir);
+  TRMPS_LAUNCH_OK("site_absorb_kernel");
+  return TRMPS_OK;
 }
 
 int launch_special_to_matrix(const float* special, float* M, int Ds, int L, cudaStream_t st) {
@@ -349,8 +386,7 @@ extern "C" int trmps_predict(const trmps_predict_desc* p, void* stream) {
       M2 += (256 - ((uintptr_t)M2 / sizeof(float)) % 256) % 256;
       float* bimg = M2 + (int64_t)4 * L * Ds * Ds;
       float* phi_far = buf[1];              // unused by the fused chains
-      special_to_bond_kernel<<<296, 256, 0, st>>>(p->special, M2, reinterpret_cast<float2*>(phi_far), Ds, L, B);
-      TRMPS_LAUNCH_OK("special_to_bond_kernel");
+      if ((rc = launch_special_to_bond(p->special, M2, phi_far, Ds, L, B, +1, st))) return rc;
       if ((rc = launch_forward_tc(buf[0], buf[2], phi_loc, phi_far, M2, bimg, fpart, B, Ds, L, p->dims + p->loc,
                                   p->dims + p->loc + 1, st)))
         return rc;

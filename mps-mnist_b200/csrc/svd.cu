@@ -695,6 +695,7 @@ struct SvdFinArgs {
   const float* M; int R, Cc, Ds; const int32_t* d_near; const int32_t* d_far; int L; const int32_t* rowmap;
   float* sv; int32_t* order; int32_t* iscal; int32_t* dim_out;
   float min_sv; int max_size, min_size;
+  int ncol_blocks;      // blocks of d_far columns that can be non-zero: 2L, or L for a bond with a unit far site
 };
 
 // squared norms of the converged rows, one warp per Jacobi rank (the whole grid reads the 2.4 MB bond; a single CTA
@@ -724,7 +725,7 @@ __global__ void __launch_bounds__(1024) svd_finalize_kernel(SvdFinArgs a) {
   if (tid == 0) s_count = 0;
   for (int p = tid; p < Ra; p += 1024) sig[p] = sqrtf(a.sv[p]);      // squared row norms by Jacobi rank (svd_rank_norms_kernel)
   __syncthreads();
-  const int kmax = min(Ra, 2 * a.L * (*a.d_far));
+  const int kmax = min(Ra, a.ncol_blocks * (*a.d_far));
   int local = 0;
   for (int p = tid; p < a.R; p += 1024) {
     if (p < Ra) {
@@ -803,7 +804,8 @@ static int launch_jacobi(SvdArgs& a, int ncta, cudaStream_t st) {
   return TRMPS_OK;
 }
 
-int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, cudaStream_t st) {
+int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, cudaStream_t st,
+              float* special_out, bool single) {
   const int Ds = s->Ds, L = s->L, R = 2 * Ds, Cc = 2 * L * Ds;
   const int blk = lay.svd_block;
   if (blk == 0) {
@@ -882,6 +884,7 @@ int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, 
   f.min_sv = opt->min_singular_value;
   f.max_size = opt->max_size < Ds ? opt->max_size : Ds;
   f.min_size = opt->min_size > 0 ? opt->min_size : 3;
+  f.ncol_blocks = single ? L : 2 * L;
   svd_rank_norms_kernel<<<(R * 32 + 255) / 256, 256, 0, st>>>(a.M, a.rowmap, a.d_near, Cc, f.sv);
   TRMPS_LAUNCH_OK("svd_rank_norms_kernel");
   svd_finalize_kernel<<<1, 1024, R * sizeof(float), st>>>(f);
@@ -891,7 +894,7 @@ int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, 
   c.M = a.M; c.Ut = a.Ut; c.R = R; c.Cc = Cc; c.Ds = Ds; c.L = L; c.dir = g.dir; c.d_near = g.d_near;
   c.order = f.order; c.rowmap = a.rowmap; c.iscal = s->iwork;
   c.node = s->nodes + (size_t)g.near_site * 2 * Ds * Ds;
-  c.special = s->special;
+  c.special = special_out ? special_out : s->special;
   svd_scatter_kernel<<<296, 256, 0, st>>>(c);
   TRMPS_LAUNCH_OK("svd_scatter_kernel");
   return TRMPS_OK;

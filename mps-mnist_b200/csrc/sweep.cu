@@ -182,6 +182,30 @@ static int check_bond(const trmps_sweep* s, int site, int dir, const char* who) 
   return TRMPS_OK;
 }
 
+// single-site update at `site` (singlesiteOptimizer.py:49-138): the "bond" is the special node alone; the far
+// environment is the one on the other side of the same site and the far site is the identity
+static BondGeom site_geom(const trmps_sweep* s, int site, int dir) {
+  BondGeom g;
+  const int64_t stride = s->B * (int64_t)s->Ds;
+  g.dir = dir;
+  g.near_site = site;
+  g.far_site = site + dir;            // the node that absorbs S V
+  if (dir > 0) {
+    g.e_near = s->envL + stride * site;
+    g.e_far = s->envR + stride * site;
+    g.d_near = s->dims + site;
+    g.d_mid = s->dims + site + 1;
+    g.d_far = s->dims + site + 1;
+  } else {
+    g.e_near = s->envR + stride * site;
+    g.e_far = s->envL + stride * site;
+    g.d_near = s->dims + site + 1;
+    g.d_mid = s->dims + site;
+    g.d_far = s->dims + site;
+  }
+  return g;
+}
+
 static int phi_pair(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, cudaStream_t st) {
   float* phi2 = s->work + lay.phi2;
   int rc = launch_phi_site(s->feat + feat_site_offset(s->feature_map, s->B, g.near_site), s->feature_map, s->B, phi2, st);
@@ -264,17 +288,16 @@ static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const Bond
   return launch_sum_red(w + lay.red, 296, 1, 1.0f / (float)s->B_total, scal + TRMPS_S_GDC, st);
 }
 
-static int do_bond_step(const trmps_sweep* s, const trmps_layout& lay, int site, int dir, const trmps_opt* opt, cudaStream_t st) {
-  const BondGeom g = bond_geom(s, site, dir);
-  const int Ds = s->Ds, L = s->L;
-  const int64_t RC = (int64_t)2 * Ds * 2 * L * Ds;
+// gradient step(s) with Armijo backtracking and accept/revert on the bond matrix in bondM (optimizer.py:239-264,
+// baseoptimizer.py:299-332); shared by the two-site and the single-site update
+static int do_update_bond(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, cudaStream_t st) {
+  const int L = s->L;
+  const int64_t RC = (int64_t)2 * s->Ds * 2 * L * s->Ds;
   float* w = s->work;
   float* scal = w + lay.scal;
   const bool hess = opt->use_hessian && s->loss_kind == TRMPS_LOSS_SOFTMAX_XENT;
   const float* delta = hess ? w + lay.deltaM : w + lay.gradM;
   int rc;
-  if ((rc = phi_pair(s, lay, g, st))) return rc;
-  if ((rc = do_merge(s, lay, g, st))) return rc;
   if ((rc = do_forward(s, lay, g, w + lay.bondM, st))) return rc;
   const int nupd = opt->updates_per_step > 0 ? opt->updates_per_step : 0;
   for (int u = 0; u < nupd; ++u) {                                  // baseoptimizer.py:324-332
@@ -290,12 +313,13 @@ static int do_bond_step(const trmps_sweep* s, const trmps_layout& lay, int site,
     if ((rc = launch_decide(scal, scal + 8, s->iwork, opt->lr, opt->armijo_coeff, st))) return rc;
     if ((rc = launch_apply_update(w + lay.bondM, delta, RC, w + lay.f0, w + lay.fd, s->B * L, scal, st))) return rc;
   }
-  {
-    ProfScope ps(PROF_SVD, st);
-    if ((rc = svd_split(s, lay, g, opt, st))) return rc;
-  }
+  return TRMPS_OK;
+}
+
+// environment advance over the site that just received its isometry (optimizer.py:187-190 / :132-135)
+static int do_env_advance(const trmps_sweep* s, int site, int dir, cudaStream_t st) {
   ProfScope ps_env(PROF_ENV, st);
-  // environment advance (optimizer.py:187-190 / :132-135)
+  const int Ds = s->Ds;
   const int64_t stride = s->B * (int64_t)Ds;
   const float* feat_site = s->feat + feat_site_offset(s->feature_map, s->B, site);
   const float* node = s->nodes + (size_t)site * 2 * Ds * Ds;
@@ -304,6 +328,53 @@ static int do_bond_step(const trmps_sweep* s, const trmps_layout& lay, int site,
                            s->envL + stride * (site + 1), st);
   return launch_env_step(feat_site, s->feature_map, s->B, Ds, -1, s->envR + stride * site, node, s->dims + site + 1,
                          s->envR + stride * (site - 1), st);
+}
+
+static int do_bond_step(const trmps_sweep* s, const trmps_layout& lay, int site, int dir, const trmps_opt* opt, cudaStream_t st) {
+  const BondGeom g = bond_geom(s, site, dir);
+  int rc;
+  if ((rc = phi_pair(s, lay, g, st))) return rc;
+  if ((rc = do_merge(s, lay, g, st))) return rc;
+  if ((rc = do_update_bond(s, lay, g, opt, st))) return rc;
+  {
+    ProfScope ps(PROF_SVD, st);
+    if ((rc = svd_split(s, lay, g, opt, st))) return rc;
+  }
+  return do_env_advance(s, site, dir, st);
+}
+
+// single-site update (singlesiteOptimizer.py:49-138): optimise the special node at `site`, split it into the
+// isometry that stays and S V, let node site+dir absorb S V (it becomes the special node), advance the environment
+static int do_site_step(const trmps_sweep* s, const trmps_layout& lay, int site, int dir, const trmps_opt* opt, cudaStream_t st) {
+  const BondGeom g = site_geom(s, site, dir);
+  const int Ds = s->Ds, L = s->L;
+  float* w = s->work;
+  if (opt->use_hessian) {
+    set_error("single-site update: the Hessian variant is not implemented (nor is it in the reference, singlesiteOptimizer.py:161-172)");
+    return TRMPS_E_ARG;
+  }
+  int rc;
+  float* phi2 = w + lay.phi2;
+  if ((rc = launch_phi_site(s->feat + feat_site_offset(s->feature_map, s->B, site), s->feature_map, s->B, phi2, st))) return rc;
+  {
+    ProfScope ps(PROF_MERGE, st);
+    if ((rc = launch_special_to_bond(s->special, w + lay.bondM, phi2 + 2 * s->B, Ds, L, s->B, dir, st))) return rc;
+  }
+  if ((rc = do_update_bond(s, lay, g, opt, st))) return rc;
+  float* tmp = w + lay.hessM;          // scratch for S V in special layout (the Hessian is off)
+  {
+    ProfScope ps(PROF_SVD, st);
+    if ((rc = svd_split(s, lay, g, opt, st, tmp, true))) return rc;
+  }
+  {
+    ProfScope ps(PROF_MERGE, st);
+    if ((rc = launch_site_absorb(tmp, s->nodes + (size_t)(site + dir) * 2 * Ds * Ds, s->special, Ds, L, dir, st))) return rc;
+  }
+  return do_env_advance(s, site, dir, st);
+}
+
+static int do_step(const trmps_sweep* s, const trmps_layout& lay, int site, int dir, const trmps_opt* opt, cudaStream_t st) {
+  return opt->single_site ? do_site_step(s, lay, site, dir, opt, st) : do_bond_step(s, lay, site, dir, opt, st);
 }
 
 static int do_init_env(const trmps_sweep* s, int loc, cudaStream_t st) {
@@ -319,7 +390,8 @@ static int do_init_env(const trmps_sweep* s, int loc, cudaStream_t st) {
     if (rc) return rc;
   }
   if ((rc = launch_fill_boundary(s->envR + stride * (N - 1), s->B, Ds, s->L, 1, st))) return rc;
-  for (int c = N - 1; c > loc + 1; --c) {
+  // down to envR[loc]: the two-site sweep needs envR[loc+1], the single-site one (singlesiteOptimizer.py:38-47) envR[loc]
+  for (int c = N - 1; c > loc; --c) {
     rc = launch_env_step(s->feat + feat_site_offset(s->feature_map, s->B, c), s->feature_map, s->B, Ds, -1, s->envR + stride * c,
                          s->nodes + slot * c, s->dims + c + 1, s->envR + stride * (c - 1), st);
     if (rc) return rc;
@@ -477,7 +549,7 @@ extern "C" int trmps_bond_step(const trmps_sweep* s, int32_t site, int32_t dir, 
   if (rc) return rc;
   if (!opt) { set_error("trmps_bond_step: null opt"); return TRMPS_E_ARG; }
   GET_LAYOUT(s, "trmps_bond_step");
-  return do_bond_step(s, lay, site, dir, opt, (cudaStream_t)stream);
+  return do_step(s, lay, site, dir, opt, (cudaStream_t)stream);
 }
 
 extern "C" int trmps_sweep_run(const trmps_sweep* s, int32_t from, int32_t to, int32_t dir, const trmps_opt* opt, void* stream) {
@@ -489,7 +561,7 @@ extern "C" int trmps_sweep_run(const trmps_sweep* s, int32_t from, int32_t to, i
   }
   GET_LAYOUT(s, "trmps_sweep_run");
   for (int c = from; c != to; c += dir) {
-    rc = do_bond_step(s, lay, c, dir, opt, (cudaStream_t)stream);
+    rc = do_step(s, lay, c, dir, opt, (cudaStream_t)stream);
     if (rc) return rc;
   }
   return TRMPS_OK;

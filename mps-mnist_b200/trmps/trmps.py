@@ -7,6 +7,7 @@ sys.path.insert(0, os.path.abspath(os.path.dirname(__file__)))
 from mps.mps import *
 from mps.squaredDistanceMPS import *
 from optimizers.optimizer import *
+from optimizers.singlesiteOptimizer import SingleSiteMPSOptimizer
 from optimizers.parameterObjects import *
 from preprocessing.preprocessing import MPSDatasource
 from preprocessing.syntheticpreprocessing import SyntheticMNISTDatasource

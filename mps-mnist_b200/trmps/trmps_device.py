@@ -247,8 +247,8 @@ class SweepState(object):
 
 
 def make_opt(lr, max_size, reg=1e-3, armijo_coeff=1e-4, min_singular_value=1e-4, updates_per_step=1,
-             use_hessian=False, min_size=3, max_svd_sweeps=0):
+             use_hessian=False, min_size=3, max_svd_sweeps=0, single_site=False):
     return nat.Opt(lr=float(lr), reg=float(reg), armijo_coeff=float(armijo_coeff),
                    min_singular_value=float(min_singular_value), max_size=int(max_size), min_size=int(min_size),
                    updates_per_step=int(updates_per_step), use_hessian=int(bool(use_hessian)),
-                   max_svd_sweeps=int(max_svd_sweeps), reserved=0)
+                   max_svd_sweeps=int(max_svd_sweeps), single_site=int(bool(single_site)))

@@ -25,7 +25,7 @@ class Opt(C.Structure):
     _fields_ = [("lr", C.c_float), ("reg", C.c_float), ("armijo_coeff", C.c_float),
                 ("min_singular_value", C.c_float), ("max_size", C.c_int32), ("min_size", C.c_int32),
                 ("updates_per_step", C.c_int32), ("use_hessian", C.c_int32),
-                ("max_svd_sweeps", C.c_int32), ("reserved", C.c_int32)]
+                ("max_svd_sweeps", C.c_int32), ("single_site", C.c_int32)]
 
 
 class Layout(C.Structure):

@@ -27,6 +27,7 @@ import trmps_oracle as o          # only for the seeded synthetic inputs and the
 
 sys.path.insert(0, REF)
 from optimizers.optimizer import MPSOptimizer                      # noqa: E402  (reference code)
+from optimizers.singlesiteOptimizer import SingleSiteMPSOptimizer  # noqa: E402
 from optimizers.parameterObjects import MPSOptimizerParameters, MPSTrainingParameters   # noqa: E402
 from mps.mps import MPS                                            # noqa: E402
 from mps.squaredDistanceMPS import sqMPS                           # noqa: E402
@@ -36,6 +37,8 @@ CASES = {
     "ref_xent_n8": (8, 96, 10, 24, None, 0.05, 0, 1, 7),
     "ref_xent_n10_loc0": (10, 64, 10, 32, 0, 0.05, 0, 1, 8),
     "ref_squared_n6": (6, 80, 10, 24, 2, 0.02, 1, 2, 9),
+    # single-site optimizer (singlesiteOptimizer.py): loss code 2 = cross-entropy, single site
+    "ref_single_n8": (8, 96, 10, 24, None, 0.05, 2, 1, 11),
 }
 
 
@@ -66,13 +69,14 @@ def reference_predict(network, weights, phi):
 def run_case(N, B, L, max_size, loc, lr, loss, updates, seed):
     pix, lab = o.synthetic_batch(N, B, L, seed=seed)
     phi = o.feature_map(pix, o.FM_ONE_SQRT3)
+    single = loss == 2
     cls = sqMPS if loss == 1 else MPS
     network = cls(2, L, N, special_node_loc=loc)
     network.prepare()                                   # default linear-model MPS (mps.py:211-219)
     f_init = reference_predict(network, None, phi)
     lr_reg = 0.99
     params = MPSOptimizerParameters(path="/tmp/ref_MPSconfig", updates_per_step=updates, lr_reg=lr_reg)
-    optimizer = MPSOptimizer(network, max_size, params)
+    optimizer = (SingleSiteMPSOptimizer if single else MPSOptimizer)(network, max_size, params)
     # train() scales the rate by 1/sqrt(1 - lr_reg^(i+1)) (baseoptimizer.py:109): undo it so that step 0 runs at `lr`
     rate0 = lr * np.sqrt(1 - lr_reg)
     optimizer.train(FixedBatch(phi, lab), B, 1, MPSTrainingParameters(rate_of_change=rate0, verbose_save=False))

@@ -418,6 +418,145 @@ def train_step(nodes, loc, feature, labels, lr, p, L, trace=None):
     return nodes
 
 
+# --------------------------------------------------------------------------- single-site DMRG
+def setup_environments_single(nodes, loc, feature, L):
+    """singlesiteOptimizer.py:9-47: C1s[0..loc], C2s[loc..N-1] (one more right environment than the two-site setup)."""
+    dtype = nodes[0].dtype
+    N, B = feature.shape[0], feature.shape[1]
+    C1s, C2s = {}, {}
+    C1 = np.tile(start_vector(L, dtype), (B, 1))
+    C1s[0] = C1
+    for c in range(0, loc):
+        C1 = chain_right(C1, feature[c], nodes[c])
+        C1s[c + 1] = C1
+    C2 = np.tile(end_vector(L, dtype), (B, 1))
+    C2s[N - 1] = C2
+    for c in range(N - 1, loc, -1):
+        C2 = chain_left(C2, feature[c], nodes[c])
+        C2s[c - 1] = C2
+    return C1s, C2s
+
+
+def calculate_C_single(C1, C2, inp):
+    """singlesiteOptimizer.py:140-152: C[t,m,i,k] = C1[t,i] C2[t,k] phi[t,m]."""
+    return np.einsum('ti,tk,tm->tmik', C1, C2, inp)
+
+
+def get_f_and_cost_single(bond, C, labels, p):
+    """singlesiteOptimizer.py:154-159 + baseoptimizer.py:347-352."""
+    f = np.tensordot(C, bond, axes=([1, 2, 3], [1, 2, 3]))
+    c = cost(f, labels, p.loss_kind)
+    h = softmax(f) if p.loss_kind == SOFTMAX_XENT else f
+    return h, c, f
+
+
+def update_bond_single(bond, C, labels, lr, p, trace=None):
+    """singlesiteOptimizer.py:174-200 (Hessian: not implemented in the reference either, :161-172)."""
+    B = C.shape[0]
+    dt = bond.dtype.type
+    h, cost0, f0 = get_f_and_cost_single(bond, C, labels, p)
+    gradient = np.tensordot(labels - h, C, axes=([0], [0])) - dt(2 * p.reg) * bond
+    delta = gradient
+    gdc = np.tensordot(gradient, delta, axes=([0, 1, 2, 3], [0, 1, 2, 3])) / dt(B)
+    counter, cond, lr_t, trials, updated = 1, True, lr, 0, bond
+    while cond and counter < 20:                       # baseoptimizer.py:299-322
+        updated = bond + dt(lr_t) * delta
+        _, c_new, _ = get_f_and_cost_single(updated, C, labels, p)
+        cond = bool(c_new > cost0 - dt(p.armijo_coeff) * dt(lr_t) * gdc)
+        if cond:
+            updated = bond
+        counter += 1
+        lr_t = lr_t * 0.5
+        trials += 1
+    _, cost1, _ = get_f_and_cost_single(updated, C, labels, p)
+    accepted = bool(cost1 < cost0)
+    if not accepted:
+        updated = bond
+    if trace is not None:
+        trace.append(dict(cost0=float(cost0), cost1=float(cost1), gdc=float(gdc), trials=trials, accepted=accepted,
+                          f0=f0, gradient=gradient))
+    return updated
+
+
+def bond_decomposition_single(bond, p, trace=None):
+    """singlesiteOptimizer.py:202-237: bond (L, d, Dl, Dr) -> a_j (d, Dl, m), a_j1 (m, L, Dr)."""
+    br = np.transpose(bond, (1, 2, 0, 3))
+    dims = br.shape
+    flat = br.reshape(dims[0] * dims[1], dims[2] * dims[3])
+    u, s, vh = np.linalg.svd(flat, full_matrices=False)
+    u = np.where(np.isnan(u), 0, u)
+    vh = np.where(np.isnan(vh), 0, vh)
+    s_size = int(np.count_nonzero(s > p.min_singular_value))
+    m = p.min_size if s_size < p.min_size else p.max_size if s_size > p.max_size else s_size
+    a_j = u[:, :m].reshape(dims[0], dims[1], -1)
+    a_j1 = (np.diag(s[:m]) @ vh[:m]).reshape(-1, dims[2], dims[3])
+    if trace is not None:
+        trace[-1]['s'] = s.copy()
+        trace[-1]['m'] = a_j.shape[2]
+    return a_j, a_j1
+
+
+def update_right_single(c, n1, nodes, C1s, C2s, feature, labels, lr, p, trace=None):
+    """singlesiteOptimizer.py:95-138: site c; the special node is split and its S V part absorbed by node c+1."""
+    C = calculate_C_single(C1s[c], C2s[c], feature[c])
+    if trace is not None:
+        trace.append_site(c, +1)
+    bond = n1
+    for _ in range(p.updates_per_step):
+        bond = update_bond_single(bond, C, labels, lr, p, trace)
+    a_j, a_j1 = bond_decomposition_single(bond, p, trace)
+    new_node = np.transpose(np.tensordot(a_j1, nodes[c + 1], axes=([2], [1])), (1, 2, 0, 3))     # (L, d, m, Dr')
+    C1s[c + 1] = chain_right(C1s[c], feature[c], a_j)
+    return a_j, new_node
+
+
+def update_left_single(c, n1, nodes, C1s, C2s, feature, labels, lr, p, trace=None):
+    """singlesiteOptimizer.py:49-93: site c moving left (bond transposed [0,1,3,2]); S V absorbed by node c-1."""
+    C = calculate_C_single(C2s[c], C1s[c], feature[c])
+    if trace is not None:
+        trace.append_site(c, -1)
+    bond = np.transpose(n1, (0, 1, 3, 2))
+    for _ in range(p.updates_per_step):
+        bond = update_bond_single(bond, C, labels, lr, p, trace)
+    a_j, a_j1 = bond_decomposition_single(bond, p, trace)
+    a_j = np.transpose(a_j, (0, 2, 1))
+    a_j1 = np.transpose(a_j1, (2, 1, 0))                                                          # (Dl, L, m)
+    new_node = np.transpose(np.tensordot(a_j1, nodes[c - 1], axes=([0], [2])), (0, 2, 3, 1))       # (L, d, Dl', m)
+    C2s[c - 1] = chain_left(C2s[c], feature[c], a_j)
+    return a_j, new_node
+
+
+def train_step_single(nodes, loc, feature, labels, lr, p, L, trace=None):
+    """baseoptimizer.py:203-244 with the single-site updates: loc -> N-1, N-1 -> 0, 0 -> loc."""
+    N = feature.shape[0]
+    dtype = nodes[0].dtype
+    feature = feature.astype(dtype, copy=False)
+    labels = labels.astype(dtype, copy=False)
+    C1s, C2s = setup_environments_single(nodes, loc, feature, L)
+    nodes = list(nodes)
+
+    def right(frm, to, nodes):
+        n1 = nodes[frm]
+        for c in range(frm, to):
+            a_j, n1 = update_right_single(c, n1, nodes, C1s, C2s, feature, labels, lr, p, trace)
+            nodes[c] = a_j
+        nodes[to] = n1
+        return nodes
+
+    def left(frm, to, nodes):
+        n1 = nodes[frm]
+        for c in range(frm, to, -1):
+            a_j, n1 = update_left_single(c, n1, nodes, C1s, C2s, feature, labels, lr, p, trace)
+            nodes[c] = a_j
+        nodes[to] = n1
+        return nodes
+
+    nodes = right(loc, N - 1, nodes)
+    nodes = left(N - 1, 0, nodes)
+    nodes = right(0, loc, nodes)
+    return nodes
+
+
 def learning_rate(initial_lr, lr_reg, step):
     """baseoptimizer.py:109."""
     return initial_lr / np.sqrt(1 - lr_reg ** (step + 1))

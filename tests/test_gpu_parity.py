@@ -308,10 +308,12 @@ def test_cuda_path_matches_reference_code_vectors(path):
     g = np.load(path)
     N, B, L, ms, loc, lr, loss, upd, seed = g['cfg']
     N, B, L, ms, loss, upd = int(N), int(B), int(L), int(ms), int(loss), int(upd)
+    single = loss == 2                      # code 2 in the generator = cross-entropy with SingleSiteMPSOptimizer
+    loss = 0 if single else loss
     nodes, loc = o.initial_nodes(N, 2, L, loc=None if loc < 0 else int(loc))
     st = make_state(N, B, L, ms, nodes, loc, g['pixels'], g['labels'], fm=nat.FM_ONE_SQRT3, loss=loss)
     assert rel(dev.predict(st.weights_view(), st.feat, nat.FM_ONE_SQRT3).cpu().numpy(), g['f_init']) < 1e-5
-    st.train_step(dev.make_opt(lr=float(lr), max_size=ms, updates_per_step=upd), loc=loc)
+    st.train_step(dev.make_opt(lr=float(lr), max_size=ms, updates_per_step=upd, single_site=single), loc=loc)
     torch.cuda.synchronize()
     assert [w.shape[-1] for w in st.get_nodes()] == g['dims'].tolist()          # bond dimensions: exact
     got = dev.predict(st.weights_view(), st.feat, nat.FM_ONE_SQRT3).cpu().numpy()
@@ -553,3 +555,74 @@ def test_bond_step_with_hessian_matches_oracle(direction):
     sv = st.singular_values().cpu().numpy()[:len(last['s'])]
     big = last['s'] > 1e-3 * last['s'][0]
     assert np.max(np.abs(sv[big] - last['s'][big]) / last['s'][big]) < RTOL
+
+
+@pytest.mark.parametrize("direction", [+1, -1])
+def test_single_site_step_matches_oracle(direction):
+    """One single-site update (singlesiteOptimizer.py:49-138) against the oracle: cost before/after, Armijo trials,
+    accept flag, kept dimension, singular values, and the function represented by the two sites afterwards."""
+    N, B, L, D, loc = 8, 400, 10, 24, 4
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=47, full_bond=D, loc=loc)
+    st = make_state(N, B, L, D, nodes, loc, phi, lab)
+    st.init_env(loc)
+    lr = 0.05
+    p = o.SweepParams(max_size=D)
+    C1s, C2s = o.setup_environments_single(nodes, loc, phi, L)
+    tr = o.Trace()
+    if direction > 0:
+        a_j, n1 = o.update_right_single(loc, nodes[loc], list(nodes), C1s, C2s, phi, lab, lr, p, tr)
+    else:
+        a_j, n1 = o.update_left_single(loc, nodes[loc], list(nodes), C1s, C2s, phi, lab, lr, p, tr)
+    st.bond_step(loc, direction, dev.make_opt(lr=lr, max_size=D, single_site=True))
+    torch.cuda.synchronize()
+    iw, sc = st.iwork.cpu().numpy(), st.scalars().cpu().numpy()
+    last = tr[-1]
+    assert int(iw[nat.I_ACCEPT]) == int(last['accepted'])
+    assert int(iw[nat.I_TRIALS]) == last['trials']
+    assert abs(sc[nat.S_COST0] - last['cost0']) < 1e-5 * abs(last['cost0'])
+    assert abs(sc[nat.S_COST1] - last['cost1']) < 1e-5 * abs(last['cost1'])
+    assert int(iw[nat.I_M]) == last['m']
+    k = len(last['s'])
+    sv = st.singular_values().cpu().numpy()[:k]
+    big = last['s'] > 1e-3 * last['s'][0]
+    assert np.max(np.abs(sv[big] - last['s'][big]) / last['s'][big]) < RTOL
+    # gauge-invariant comparison: the product of the isometry left behind and the new special node
+    got_nodes = st.get_nodes()
+    if direction > 0:
+        got = np.einsum('miq,lnqk->lmnik', got_nodes[loc], got_nodes[loc + 1])
+        want = np.einsum('miq,lnqk->lmnik', a_j, n1)
+    else:
+        got = np.einsum('lnkq,mqi->lnmki', got_nodes[loc - 1], got_nodes[loc])
+        want = np.einsum('lnkq,mqi->lnmki', n1, a_j)
+    assert rel(got, want) < RTOL
+
+
+def test_single_site_train_step_matches_oracle():
+    N, B, L, ms = 8, 300, 10, 24
+    pix, phi, lab, nodes, loc = make_case(N, B, L, ms, seed=53)
+    p = o.SweepParams(max_size=ms)
+    want_nodes = o.train_step_single(nodes, loc, phi, lab, 0.05, p, L)
+    want_f = o.predict(want_nodes, loc, phi, L)
+    st = make_state(N, B, L, ms, nodes, loc, phi, lab)
+    st.train_step(dev.make_opt(lr=0.05, max_size=ms, single_site=True), loc=loc)
+    torch.cuda.synchronize()
+    got_nodes = st.get_nodes()
+    assert [w.shape for w in got_nodes] == [w.shape for w in want_nodes]
+    got_f = dev.predict(st.weights_view(), st.feat, nat.FM_PRECOMPUTED).cpu().numpy()
+    assert rel(got_f, want_f) < 3e-3                 # chained fp32 updates, as for the two-site step
+    assert abs(o.cost(got_f, lab) - o.cost(want_f, lab)) < 1e-3 * o.cost(want_f, lab)
+
+
+def test_single_site_optimizer_class_trains(tmp_path):
+    from trmps import MPS, SingleSiteMPSOptimizer, MPSOptimizerParameters, MPSTrainingParameters, SyntheticMNISTDatasource
+    ds = SyntheticMNISTDatasource(shrink=True, n_train=400, n_test=100, seed=2)
+    net = MPS(2, 10, 196)
+    net.prepare(ds, iterations=50, learning_rate=0.05)
+    opt = SingleSiteMPSOptimizer(net, 16, MPSOptimizerParameters(path=str(tmp_path / "cfg"), reg=1e-3))
+    c0 = net.cost(net.predict(ds.training_data[0]), ds.training_data[1])
+    opt.train(ds, 400, 1, MPSTrainingParameters(rate_of_change=1e-2, verbose_save=False))
+    assert len(opt.test) == 196
+    assert net.cost(net.predict(ds.training_data[0]), ds.training_data[1]) < c0
+    with pytest.raises(ValueError):
+        SingleSiteMPSOptimizer(net, 16, MPSOptimizerParameters(path=str(tmp_path / "cfg2"), use_hessian=True)).train(
+            ds, 400, 1, MPSTrainingParameters(rate_of_change=1e-2, verbose_save=False))

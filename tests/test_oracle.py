@@ -57,7 +57,10 @@ def test_oracle_matches_reference_code_run_under_tf_shim(path):
     nodes, loc = o.initial_nodes(N, 2, L, loc=loc)
     assert loc == int(g['loc'])
     assert rel(o.predict(nodes, loc, phi, L), g['f_init']) < 1e-6
-    new = o.train_step(nodes, loc, phi, lab, lr, o.SweepParams(max_size=ms, updates_per_step=upd, loss_kind=loss), L)
+    single = loss == 2                      # generator code 2 = cross-entropy with the reference's SingleSiteMPSOptimizer
+    loss = 0 if single else loss
+    step = o.train_step_single if single else o.train_step
+    new = step(nodes, loc, phi, lab, lr, o.SweepParams(max_size=ms, updates_per_step=upd, loss_kind=loss), L)
     assert [w.shape[-1] for w in new] == g['dims'].tolist()
     f = o.predict(new, loc, phi, L)
     assert rel(f, g['f_final']) < 1e-5
