@@ -168,6 +168,18 @@ def cpu_inference_rate(B_s, N, D, L, seed=0):
     return B_s / dt, dt
 
 
+def cpu_fetch_rate(B_s, seed=0):
+    """The datasource side on the host: oracle average pool + batch slice + the swapaxes copy the reference makes per step."""
+    import trmps_oracle as o
+    images = np.random.default_rng(seed).random((B_s, 784), dtype=np.float32)
+    t0 = time.perf_counter()
+    pooled = o.preprocess_images(images, 28, 28, True, o.FM_PRECOMPUTED)
+    feat, _, _ = o.next_batch(pooled, np.zeros((B_s, 1), np.float32), 0, B_s)
+    np.ascontiguousarray(feat)
+    dt = time.perf_counter() - t0
+    return B_s / dt, dt
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -332,11 +344,53 @@ def run_ours(args, rank, local_rank, world):
         inference = inference_rate(N, D, b3, "cfg3")
         torch.cuda.empty_cache()
         inference_cfg5 = inference_rate(784, 32, args.inference_images, "cfg5")
+
+    # datasource side of the path: one fused launch per batch fetch -- slice, 2x2 average pool and
+    # (B, pixels) -> (N, B) transposition -- from raw float32 images resident in HBM.  HBM bound: bytes = images read + batch written.
+    def fetch_rate(Bi, shrink, label):
+        gen = torch.Generator(device=device).manual_seed(11 + rank)
+        imgs = torch.rand((Bi, 784), device=device, generator=gen)
+        n_sites = 196 if shrink else 784
+        outp = torch.empty((n_sites, Bi), device=device)
+        for _ in range(3):
+            dev.preprocess_batch(imgs, 28, 28, shrink, 0, Bi, out=outp)
+        barrier()
+        reps = 20
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for r_ in range(reps):
+            dev.preprocess_batch(imgs, 28, 28, shrink, (r_ * 977) % Bi, Bi, out=outp)
+        p1.record()
+        barrier()
+        pms = torch.tensor([p0.elapsed_time(p1) / reps], device=device)
+        if world > 1:
+            dist.all_reduce(pms, op=dist.ReduceOp.MAX)
+        pms = float(pms.item())
+        nbytes = Bi * 4.0 * (784 + n_sites)
+        return dict(kernel="preprocess_%s_kernel<float>" % ("pool" if shrink else "flat"), bound="hbm",
+                    workload="%s: %d float32 28x28 images per GPU -> (%d, B) site-major pixels%s" %
+                             (label, Bi, n_sites, ", 2x2 average pool" if shrink else ""),
+                    images_per_sec=world * Bi / (pms * 1e-3), ms_per_launch=pms, bytes_per_launch=nbytes,
+                    achieved=nbytes / (pms * 1e-3) / 1e9, unit="GB/s",
+                    l2="%.0f MB per launch, larger than L2" % (nbytes / 1e6),
+                    # ncu --set full of the same launches (profiles/r1l_datasource_kernels_ncu.txt): dram read + write
+                    traffic={(60000, True): 0.188180e9 + 0.023254e9, (1000000, False): 3.136021e9 + 3.087183e9}.get((Bi, shrink)),
+                    traffic_source="ncu dram__bytes_read+write per launch (profiles/r1l_datasource_kernels_ncu.txt): the algorithmic "
+                                   "bytes, no re-reads; part of a 60k-image batch's output is still in L2 when the kernel ends")
+
+    datasource = None
+    if not args.no_inference:
+        torch.cuda.empty_cache()
+        datasource = [fetch_rate(B, True, "cfg3 batch fetch"), fetch_rate(args.inference_images, False, "cfg5 batch fetch")]
+        torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peaks = measured_peaks()
+    if datasource:
+        for d_ in datasource:
+            d_.update(peak=peaks["hbm_gbs"], frac=d_["achieved"] / peaks["hbm_gbs"], peak_source="%s HBM copy bandwidth" % peaks["source"])
     tf32_peak = peaks["bf16_sustained"] / 2.0       # TF32 dense = bf16 / 2, kernel timed inside a long step
     fwd_ms, fwd_n = prof["forward"]
     flops_per_launch = 2.0 * B * L * 4 * D * D     # one 2*L*d^2*Dl*Dr contraction per image
@@ -387,7 +441,8 @@ def run_ours(args, rank, local_rank, world):
                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                         steps=args.e2e_steps, last_cost=last_cost),
                roofline=roofline_svd, roofline_forward=roofline_fwd,
-               breakdown_ms_per_step=breakdown, inference=inference, inference_cfg5=inference_cfg5)
+               breakdown_ms_per_step=breakdown, inference=inference, inference_cfg5=inference_cfg5,
+               roofline_datasource=datasource)
     if world == 1 and not args.no_cpu_baseline:
         r, dt, cores = cpu_sweep_rate(args.cpu_sample_images, args.cpu_sample_bonds, D, L)
         out["cpu_baseline"] = dict(value=r, unit=UNIT, cores=cores, kind="port",
@@ -397,6 +452,9 @@ def run_ours(args, rank, local_rank, world):
             ri, dti = cpu_inference_rate(4000, N, D, L)
             out["cpu_baseline"].update(inference_value=ri, inference_unit="images/s",
                                        inference_sample="cfg3 predict on 4000 images (%.1f s), NumPy chain" % dti)
+            rf, dtf = cpu_fetch_rate(60000)
+            out["cpu_baseline"].update(fetch_value=rf, fetch_unit="images/s",
+                                       fetch_sample="cfg3 batch fetch of 60000 images (%.2f s): NumPy average pool + slice + swapaxes copy" % dtf)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

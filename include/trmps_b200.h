@@ -53,6 +53,10 @@ extern "C" {
 #define TRMPS_FM_ONE_X       2    /* [1, x]  FashionMNISTpreprocessing.py:73 */
 #define TRMPS_FM_COS_SIN     3    /* [cos(pi x/2), sin(pi x/2)]  north_star benchmark map */
 
+/* element types of raw image buffers handed to trmps_preprocess_batch */
+#define TRMPS_DT_F32 0            /* float32 pixels in [0,1] (what the TF-1.2 MNIST loader returns) */
+#define TRMPS_DT_U8  1            /* uint8 pixels as stored in the idx files; scaled by 1/255 in float32 like the loader does */
+
 /* loss kinds */
 #define TRMPS_LOSS_SOFTMAX_XENT 0 /* MPS.cost  mps.py:267-280, residual y - softmax(f) */
 #define TRMPS_LOSS_SQUARED      1 /* sqMPS.cost squaredDistanceMPS.py:15-27, residual y - f */
@@ -156,7 +160,8 @@ typedef struct {
 int         trmps_abi_version(void);
 const char* trmps_last_error(void);
 int         trmps_device_check(int device);             /* TRMPS_OK if `device` is an sm_100 GPU */
-int         trmps_set_option(int32_t option, int32_t value); /* option 0: gradient kernel, 1: forward kernel, 2: inference chain; value 0 = tcgen05 3xTF32 (default), 1 = FP32 SIMT */
+int         trmps_set_option(int32_t option, int32_t value); /* option 0: gradient kernel, 1: forward kernel, 2: inference chain; value 0 = tcgen05 (default), 1 = FP32 SIMT;
+                                                            option 3: tile shape of the flat datasource kernel (development switch, 0 = default) */
 int64_t     trmps_launch_count(void);                   /* kernels launched by this library so far (process-wide) */
 
 /* optional device-side timing of the kernels a sweep launches (CUDA events on the caller's stream; replaces the
@@ -173,6 +178,22 @@ int64_t trmps_predict_work_floats(int64_t B, int32_t L, int32_t Ds, int32_t N);
 
 /* phi = feature_map(pixels): the datasource-side map, MNISTpreprocessing.py:55.  out (N*B, 2). */
 int trmps_feature_map(const float* pixels, int64_t count, int32_t feature_map, float* phi_out, void* stream);
+
+/* Datasource-side preprocessing fused with the batch fetch.  Replaces the per-image sess.run loop
+ * of _preprocess_images (MNISTpreprocessing.py:14-78: 2x2 average pool :44-48 when `shrink`, flatten, feature map :55) and
+ * the slice + wrap-around + swapaxes(0,1) of MPSDatasource.next_training_data_batch (preprocessing.py:165-208).
+ * images: (total, rows*cols) row-major, float32 or uint8 (TRMPS_DT_*).  The batch is images[(start + t) % total], t < B.
+ * out_map = TRMPS_FM_PRECOMPUTED: out is (N, B) pooled pixels (for the kernels' fused maps); otherwise out is
+ * (N, B, 2) phi of that map.  N = rows*cols/4 with shrink (rows even, cols % 4 == 0, cols <= 64), rows*cols without
+ * (any shape; rows*cols % 4 == 0 takes the 16-byte load path). */
+int trmps_preprocess_batch(const void* images, int32_t dtype, int64_t total, int32_t rows, int32_t cols, int32_t shrink,
+                           int64_t start, int64_t B, int32_t out_map, float* out, void* stream);
+
+/* MPSDatasource.next_training_data_batch (preprocessing.py:165-208) on a device-resident dataset in the reference's
+ * storage layout: data (total, N, c) with c = 2 (phi) or 1 (pixels), labels (total, L) or NULL.
+ * feat_out (N, B, c), labels_out (B, L); rows (start + t) % total. */
+int trmps_batch_gather(const float* data, const float* labels, int64_t total, int32_t N, int32_t c, int32_t L,
+                       int64_t start, int64_t B, float* feat_out, float* labels_out, void* stream);
 
 /* one environment step, _chain_multiply_r/_l (mps.py:500-519), _find_C1/_find_C2 (baseoptimizer.py:160-201).
  * dir=+1: out[t,j] = sum_{m,i} phi[t,m] in[t,i] node[m,i,j];  dir=-1: out[t,i] = sum_{m,j} phi[t,m] node[m,i,j] in[t,j].

@@ -188,6 +188,7 @@ int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, 
               float* special_out = nullptr, bool single = false);
 int launch_special_to_bond(const float* special, float* M, float* phi_far, int Ds, int L, int64_t B, int dir, cudaStream_t st);
 int launch_site_absorb(const float* tmp, const float* node, float* special, int Ds, int L, int dir, cudaStream_t st);
+void set_flat_variant(int v);   // development switch: tile shape of the flat datasource kernel
 int allreduce_sum(void* comm, float* buf, int64_t count, cudaStream_t st);
 
 }  // namespace trmps

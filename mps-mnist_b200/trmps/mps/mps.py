@@ -84,9 +84,11 @@ class MPS(object):
         b = torch.zeros((self.d_output,), dtype=torch.float32, device=tdev)
         for _ in range(int(iterations)):
             feat, lab = data_source.next_training_data_batch(100)
-            x = torch.as_tensor(np.ascontiguousarray(feat), dtype=torch.float32, device=tdev)[:, :, 1:]
+            if not isinstance(feat, torch.Tensor):                  # device-resident datasources hand out CUDA tensors
+                feat, lab = np.ascontiguousarray(feat), np.asarray(lab)
+            x = torch.as_tensor(feat, dtype=torch.float32, device=tdev)[:, :, 1:]
             x = x.permute(1, 0, 2).reshape(x.shape[1], n_in)
-            y = torch.as_tensor(np.asarray(lab), dtype=torch.float32, device=tdev)
+            y = torch.as_tensor(lab, dtype=torch.float32, device=tdev)
             z = x @ W + b
             gz = self._lin_reg_grad(z, y)
             W -= learning_rate * (x.t() @ gz)

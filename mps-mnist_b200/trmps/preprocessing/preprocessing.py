@@ -4,6 +4,9 @@ Data is held as ([batch, input_size, d_feature], [batch, classes]); the model-fa
 the features with the first two axes swapped, (input_size, batch, d_feature), as the MPS expects.
 """
 import os
+import sys
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), '..')))
 
 import numpy as np
 
@@ -38,6 +41,18 @@ class MPSDatasource(object):
             self.shuffle()
         self._swapped_test_data = None
         self._swapped_training_data = None
+        self._device_training = None
+
+    def to_device(self, device=None):
+        """Keep the training set resident on the GPU in its storage layout ([batch, input_size, d], [batch, classes]).
+        next_training_data_batch then returns CUDA tensors produced by one trmps_batch_gather launch (slice, wrap-around
+        and the (batch, N, d) -> (N, batch, d) swap of preprocessing.py:165-208) instead of a NumPy copy per step."""
+        import torch
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        data, labels = self._training_data
+        self._device_training = (torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(device),
+                                 torch.from_numpy(np.ascontiguousarray(labels, dtype=np.float32)).to(device))
+        return self
 
     def _cached(self, data_path, labels_path):
         # preprocessing.py:39-53: reuse the cache only if an element has the expected shape
@@ -84,6 +99,8 @@ class MPSDatasource(object):
         order = np.random.permutation(len(data))
         self._training_data = data[order], labels[order]
         self._swapped_training_data = None
+        if getattr(self, "_device_training", None) is not None:
+            self.to_device(self._device_training[0].device)
 
     def next_training_data_batch(self, batch_size):
         """Next batch_size samples in dataset order, wrapping around at the end and carrying the read
@@ -94,6 +111,13 @@ class MPSDatasource(object):
         total = len(all_data)
         if batch_size > total:
             print("Probably shouldn't do this; your batch size is greater than the size of the dataset")
+        if self._device_training is not None:
+            import trmps_device as dev
+            start = self.current_index % total
+            feature, labels = dev.batch_gather(self._device_training[0], self._device_training[1], start, batch_size)
+            # where the reference's loop leaves the read position (it stays at `total` after an exact fit)
+            self.current_index = (start + batch_size) % total or (total if batch_size else start)
+            return feature, labels
         pieces_x, pieces_y = [], []
         remaining = batch_size
         while remaining > 0:

@@ -84,6 +84,60 @@ def feature_layout(feature, N, d):
     raise ValueError("feature must be (N=%d, B, d=%d) phi or (N, B) pixels; got %r" % (N, d, shp))
 
 
+def preprocess_batch(images, rows, cols, shrink, start, batch, out_map=nat.FM_PRECOMPUTED, out=None):
+    """Fused datasource preprocessing + batch fetch on the device (MNISTpreprocessing.py:44-55, preprocessing.py:165-208).
+    images: CUDA tensor (total, rows*cols), float32 in [0,1] or uint8.  Returns (N, batch) pooled pixels when
+    out_map == FM_PRECOMPUTED, else (N, batch, 2) phi of that map; the batch is images[(start + t) % total]."""
+    if not (isinstance(images, torch.Tensor) and images.is_cuda and images.is_contiguous()):
+        raise ValueError("preprocess_batch: images must be a contiguous CUDA tensor")
+    if images.dtype not in (torch.float32, torch.uint8):
+        raise ValueError("preprocess_batch: images must be float32 or uint8")
+    total = images.shape[0]
+    if images.numel() != total * rows * cols:
+        raise ValueError("preprocess_batch: images must be (total, rows*cols)")
+    n_sites = (rows // 2) * (cols // 2) if shrink else rows * cols
+    shape = (n_sites, batch) if out_map == nat.FM_PRECOMPUTED else (n_sites, batch, 2)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=images.device)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("preprocess_batch: out must be a contiguous float32 tensor of shape %r" % (shape,))
+    dt = nat.DT_F32 if images.dtype == torch.float32 else nat.DT_U8
+    if batch == 0:
+        return out
+    nat.check(nat.load().trmps_preprocess_batch(images.data_ptr(), dt, total, rows, cols, int(bool(shrink)), int(start),
+                                                int(batch), int(out_map), out.data_ptr(), _stream_ptr()),
+              "trmps_preprocess_batch")
+    return out
+
+
+def batch_gather(data, labels, start, batch, feat_out=None, labels_out=None):
+    """MPSDatasource.next_training_data_batch (preprocessing.py:165-208) on a device-resident dataset:
+    data (total, N, c) or (total, N) float32 CUDA, labels (total, L) float32 CUDA or None.
+    Returns feat (N, batch[, c]) and labels (batch, L) for rows (start + t) % total."""
+    if not (isinstance(data, torch.Tensor) and data.is_cuda and data.is_contiguous() and data.dtype == torch.float32):
+        raise ValueError("batch_gather: data must be a contiguous float32 CUDA tensor")
+    total, N = data.shape[0], data.shape[1]
+    c = data.shape[2] if data.dim() == 3 else 1
+    shape = (N, batch, c) if data.dim() == 3 else (N, batch)
+    if feat_out is None:
+        feat_out = torch.empty(shape, dtype=torch.float32, device=data.device)
+    elif tuple(feat_out.shape) != shape or not feat_out.is_contiguous():
+        raise ValueError("batch_gather: feat_out must be contiguous with shape %r" % (shape,))
+    L, lab_ptr, lab_out_ptr = 0, None, None
+    if labels is not None:
+        if not (labels.is_cuda and labels.is_contiguous() and labels.dtype == torch.float32 and labels.shape[0] == total):
+            raise ValueError("batch_gather: labels must be a contiguous float32 CUDA tensor (total, L)")
+        L = labels.shape[1]
+        if labels_out is None:
+            labels_out = torch.empty((batch, L), dtype=torch.float32, device=data.device)
+        lab_ptr, lab_out_ptr = labels.data_ptr(), labels_out.data_ptr()
+    if batch == 0:
+        return feat_out, labels_out
+    nat.check(nat.load().trmps_batch_gather(data.data_ptr(), lab_ptr, total, N, c, L, int(start), int(batch),
+                                            feat_out.data_ptr(), lab_out_ptr, _stream_ptr()), "trmps_batch_gather")
+    return feat_out, labels_out
+
+
 class DeviceWeights(object):
     """MPS weights resident on the GPU in slot layout."""
 

@@ -93,8 +93,47 @@ def run_case(N, B, L, max_size, loc, lr, loss, updates, seed):
                 cfg=np.array([x if x is not None else -1 for x in (N, B, L, max_size, loc, lr, loss, updates, seed)], dtype=np.float64))
 
 
+class FakeMnistSplit(object):
+    """Stands in for `read_data_sets(...).train`: next_batch(n, shuffle=False) of the TF-1.2 loader (consecutive samples,
+    wrapping to the start of the set), on seeded uint8 images scaled by 1/255 like DataSet.__init__ does."""
+
+    def __init__(self, images_u8, labels):
+        self.images = o.scale_uint8(images_u8)
+        self.labels = labels
+        self.pos = 0
+
+    def next_batch(self, n, shuffle=True):
+        assert shuffle is False                      # MNISTpreprocessing.py:68
+        rows = (self.pos + np.arange(n)) % len(self.images)
+        self.pos = (self.pos + n) % len(self.images)
+        return self.images[rows], self.labels[rows]
+
+
+def run_preprocess_case(seed=21, count=26, size=40):
+    """The reference's own _preprocess_images (MNISTpreprocessing.py:14-78), shrink on and off, on `count` seeded 28x28
+    uint8 images; size > count so the loader wraps around."""
+    from preprocessing.MNISTpreprocessing import _preprocess_images       # reference code
+    rng = np.random.default_rng(seed)
+    images = rng.integers(0, 256, (count, 784), dtype=np.uint8)
+    images[0, :28] = 0
+    images[1, :28] = 255
+    labels = np.eye(10)[rng.integers(0, 10, count)]
+    rec = dict(images_u8=images, labels=labels, size=np.int32(size))
+    for shrink in (True, False):
+        data, lab = _preprocess_images(FakeMnistSplit(images, labels), size, shrink=shrink)
+        assert data.dtype == np.float32 and np.all(data[..., 0] == 1)
+        rec["phi1_shrink" if shrink else "phi1_full"] = data[..., 1]       # phi[..., 0] is the constant 1
+        rec["labels_out"] = lab
+    return rec
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        rec = run_preprocess_case()
+    np.savez_compressed(os.path.join(OUT, "ref_preprocess.npz"), **rec)
+    print("ref_preprocess", rec["phi1_shrink"].shape, rec["phi1_full"].shape)
     for name, cfg in CASES.items():
         sink = io.StringIO()
         with contextlib.redirect_stdout(sink):            # the reference prints a lot

@@ -342,7 +342,18 @@ def _softmax_xent(labels=None, logits=None, name=None, dim=-1):
     return Tensor(fn)
 
 
-nn = types.SimpleNamespace(softmax=_op(_softmax), softmax_cross_entropy_with_logits=_softmax_xent)
+def _avg_pool(value, ksize=None, strides=None, padding=None, data_format="NHWC"):
+    """NHWC average pooling for the one configuration the reference uses (2x2 window, stride 2, even extents:
+    MNISTpreprocessing.py:44-45); the window is summed row by row, left to right, in float32."""
+    if list(ksize) != [1, 2, 2, 1] or list(strides) != [1, 2, 2, 1]:
+        raise NotImplementedError("tf1_shim avg_pool: only ksize = strides = [1,2,2,1]")
+    x = np.asarray(value)
+    b, h, w, c = x.shape
+    x = x.reshape(b, h // 2, 2, w // 2, 2, c)
+    return ((x[:, :, 0, :, 0] + x[:, :, 0, :, 1]) + (x[:, :, 1, :, 0] + x[:, :, 1, :, 1])) * x.dtype.type(0.25)
+
+
+nn = types.SimpleNamespace(softmax=_op(_softmax), softmax_cross_entropy_with_logits=_softmax_xent, avg_pool=_op(_avg_pool))
 contrib = types.SimpleNamespace(layers=types.SimpleNamespace(flatten=_op(lambda a: np.reshape(a, (np.shape(a)[0], -1)))))
 
 
@@ -411,6 +422,10 @@ def install():
     sys.modules["tensorflow.python"] = pkg_python
     sys.modules["tensorflow.python.client"] = pkg_client
     sys.modules["tensorflow.python.client.timeline"] = timeline_mod
+    # trmps/preprocessing/MNISTpreprocessing.py:12 imports the tutorial loader at module level (it downloads MNIST)
+    for name in ("tensorflow.examples", "tensorflow.examples.tutorials", "tensorflow.examples.tutorials.mnist"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["tensorflow.examples.tutorials.mnist"].input_data = types.SimpleNamespace(read_data_sets=_NotAvailable)
     try:
         import matplotlib.pyplot  # noqa: F401
     except Exception:

@@ -50,6 +50,53 @@ def feature_map(pixels, kind, dtype=np.float32):
     raise ValueError("unknown feature map %r" % (kind,))
 
 
+# --------------------------------------------------------------------------- datasource side
+def scale_uint8(images_u8):
+    """uint8 idx pixels -> float32 in [0,1] as the TF-1.2 MNIST loader does it (tensorflow/contrib/learn/python/learn/
+    datasets/mnist.py, DataSet.__init__: astype(float32) then multiply by 1.0 / 255.0; un-vendored dependency of
+    MNISTpreprocessing.py:12, restated from its published source)."""
+    return np.multiply(np.asarray(images_u8).astype(np.float32), 1.0 / 255.0)
+
+
+def avg_pool_2x2(images, rows, cols):
+    """tf.nn.avg_pool(ksize=[1,2,2,1], strides=[1,2,2,1], 'SAME') + reshape to [rows/2 * cols/2]
+    (MNISTpreprocessing.py:44-48) for even rows/cols.  (B, rows*cols) -> (B, rows*cols/4), float32.
+    Summation order inside a window: (top-left + top-right) + (bottom-left + bottom-right); TensorFlow's own order is
+    not pinned (at most one ulp apart)."""
+    x = np.asarray(images, dtype=np.float32).reshape(-1, rows // 2, 2, cols // 2, 2)
+    top = x[:, :, 0, :, 0] + x[:, :, 0, :, 1]
+    bottom = x[:, :, 1, :, 0] + x[:, :, 1, :, 1]
+    return ((top + bottom) * np.float32(0.25)).reshape(x.shape[0], -1)
+
+
+def feature_map_f32(x, kind):
+    """The feature maps evaluated the way a float32 TF graph does (constants cast to float32 first):
+    MNISTpreprocessing.py:55, FashionMNISTpreprocessing.py:73.  (...,) -> (..., 2)."""
+    x = np.asarray(x, dtype=np.float32)
+    if kind == FM_ONE_SQRT3:
+        return np.stack([np.ones_like(x), np.float32(np.sqrt(3)) * (np.float32(2) * x - np.float32(1))], axis=-1)
+    return feature_map(x, kind)
+
+
+def preprocess_images(images, rows, cols, shrink, kind=FM_ONE_SQRT3):
+    """_preprocess_images (MNISTpreprocessing.py:14-78) for a whole array of images instead of one sess.run per image:
+    (B, rows*cols) float32 -> (B, N, 2) phi in the datasource's storage layout; kind = FM_PRECOMPUTED returns the
+    (B, N) pooled pixels."""
+    x = np.asarray(images, dtype=np.float32).reshape(len(images), rows * cols)
+    if shrink:
+        x = avg_pool_2x2(x, rows, cols)
+    return x if kind == FM_PRECOMPUTED else feature_map_f32(x, kind)
+
+
+def next_batch(data, labels, start, batch_size):
+    """MPSDatasource.next_training_data_batch (preprocessing.py:165-208): batch_size consecutive samples from `start`,
+    wrapping to index 0 at the end of the dataset; features with the first two axes swapped.
+    -> ((N, B, ...), (B, L), next start)."""
+    total = len(data)
+    rows = (start + np.arange(batch_size)) % total
+    return np.swapaxes(data[rows], 0, 1), labels[rows], int((start + batch_size) % total)
+
+
 # --------------------------------------------------------------------------- initial MPS
 def start_vector(L, dtype=np.float32):
     """trmps/mps/mps.py:446-454  [0_L, 1_L]"""

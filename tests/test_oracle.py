@@ -10,7 +10,9 @@ import trmps_oracle as o
 
 ALL_NPZ = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 GOLDEN = [p for p in ALL_NPZ if not os.path.basename(p).startswith("ref_")]     # written by oracle/make_golden.py
-REF_GOLDEN = [p for p in ALL_NPZ if os.path.basename(p).startswith("ref_")]     # written by the REFERENCE code under oracle/tf1_shim.py
+REF_GOLDEN = [p for p in ALL_NPZ if os.path.basename(p).startswith("ref_")      # written by the REFERENCE code under oracle/tf1_shim.py
+              and os.path.basename(p) != "ref_preprocess.npz"]                   # (sweep cases; the datasource case has its own test)
+GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def rel(a, b):
@@ -176,3 +178,40 @@ def test_feature_maps():
     cs = o.feature_map(x, o.FM_COS_SIN)[0]
     assert np.allclose(cs, [[1, 0], [np.sqrt(0.5), np.sqrt(0.5)], [0, 1]], atol=1e-6)
     assert np.allclose((cs ** 2).sum(-1), 1, atol=1e-6)
+
+
+def test_datasource_oracle_matches_reference_preprocessing_code():
+    """o.preprocess_images / o.next_batch against what the reference's own _preprocess_images (MNISTpreprocessing.py:14-78,
+    run under the TF shim on a stand-in for the TF loader) returned: bit for bit, wrap-around included."""
+    g = np.load(os.path.join(GOLDEN_DIR, "ref_preprocess.npz"))
+    images = o.scale_uint8(g["images_u8"])
+    size = int(g["size"])
+    rows = np.arange(size) % len(images)
+    for shrink, key in ((True, "phi1_shrink"), (False, "phi1_full")):
+        phi = o.preprocess_images(images, 28, 28, shrink, o.FM_ONE_SQRT3)
+        assert phi.dtype == np.float32 and np.all(phi[..., 0] == 1)
+        assert np.array_equal(phi[rows][..., 1], g[key])
+        feat, lab, nxt = o.next_batch(phi, g["labels"], 0, size)
+        assert np.array_equal(feat[..., 1].T, g[key]) and np.array_equal(lab, g["labels_out"])
+        assert nxt == size % len(images)
+    pooled = o.preprocess_images(images, 28, 28, True, o.FM_PRECOMPUTED)
+    assert np.allclose(pooled, images.reshape(-1, 14, 2, 14, 2).mean(axis=(2, 4)).reshape(-1, 196), atol=1e-7)
+
+
+def test_next_batch_oracle_follows_the_reference_datasource():
+    """o.next_batch against the mirror of MPSDatasource.next_training_data_batch (preprocessing.py:165-208) over a
+    sequence of batch sizes that wraps, fits exactly and exceeds the dataset."""
+    from preprocessing.preprocessing import MPSDatasource
+
+    class DS(MPSDatasource):
+        _use_cache_dir = False
+
+    rng = np.random.default_rng(0)
+    data, labels = rng.normal(size=(23, 6, 2)).astype(np.float32), np.eye(4)[rng.integers(0, 4, 23)]
+    ds = DS((6, 2), False, _training_data=(data, labels), _test_data=(data, labels))
+    start = 0
+    for batch in (5, 18, 10, 23, 50, 1):
+        got_f, got_l = ds.next_training_data_batch(batch)
+        want_f, want_l, start = o.next_batch(data, labels, start, batch)
+        assert np.array_equal(got_f, want_f) and np.array_equal(got_l, want_l)
+        assert ds.current_index % 23 == start
