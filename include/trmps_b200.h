@@ -56,6 +56,12 @@ extern "C" {
 /* element types of raw image buffers handed to trmps_preprocess_batch */
 #define TRMPS_DT_F32 0            /* float32 pixels in [0,1] (what the TF-1.2 MNIST loader returns) */
 #define TRMPS_DT_U8  1            /* uint8 pixels as stored in the idx files; scaled by 1/255 in float32 like the loader does */
+#define TRMPS_DT_U8_DIV 2         /* uint8 pixels divided by 255 (correctly rounded): FashionMNISTpreprocessing.py:60 */
+
+/* pooling applied by trmps_preprocess_batch (the datasources' `shrink`) */
+#define TRMPS_POOL_NONE 0         /* shrink=False */
+#define TRMPS_POOL_AVG  1         /* 2x2 average, MNISTpreprocessing.py:44-45 */
+#define TRMPS_POOL_MAX  2         /* 2x2 maximum, FashionMNISTpreprocessing.py:61-65 */
 
 /* loss kinds */
 #define TRMPS_LOSS_SOFTMAX_XENT 0 /* MPS.cost  mps.py:267-280, residual y - softmax(f) */
@@ -180,13 +186,15 @@ int64_t trmps_predict_work_floats(int64_t B, int32_t L, int32_t Ds, int32_t N);
 int trmps_feature_map(const float* pixels, int64_t count, int32_t feature_map, float* phi_out, void* stream);
 
 /* Datasource-side preprocessing fused with the batch fetch.  Replaces the per-image sess.run loop
- * of _preprocess_images (MNISTpreprocessing.py:14-78: 2x2 average pool :44-48 when `shrink`, flatten, feature map :55) and
+ * of _preprocess_images (MNISTpreprocessing.py:14-78: 2x2 average pool :44-48 when `shrink`, flatten, feature map :55), the
+ * Fashion-MNIST variant (FashionMNISTpreprocessing.py:56-77: /255, 2x2 maximum, [1, x]) and
  * the slice + wrap-around + swapaxes(0,1) of MPSDatasource.next_training_data_batch (preprocessing.py:165-208).
- * images: (total, rows*cols) row-major, float32 or uint8 (TRMPS_DT_*).  The batch is images[(start + t) % total], t < B.
+ * images: (total, rows*cols) row-major, float32 or uint8 (TRMPS_DT_*); pool: TRMPS_POOL_*.  The batch is
+ * images[(start + t) % total], t < B.
  * out_map = TRMPS_FM_PRECOMPUTED: out is (N, B) pooled pixels (for the kernels' fused maps); otherwise out is
- * (N, B, 2) phi of that map.  N = rows*cols/4 with shrink (rows even, cols % 4 == 0, cols <= 64), rows*cols without
+ * (N, B, 2) phi of that map.  N = rows*cols/4 with pooling (rows even, cols % 4 == 0, cols <= 64), rows*cols without
  * (any shape; rows*cols % 4 == 0 takes the 16-byte load path). */
-int trmps_preprocess_batch(const void* images, int32_t dtype, int64_t total, int32_t rows, int32_t cols, int32_t shrink,
+int trmps_preprocess_batch(const void* images, int32_t dtype, int64_t total, int32_t rows, int32_t cols, int32_t pool,
                            int64_t start, int64_t B, int32_t out_map, float* out, void* stream);
 
 /* MPSDatasource.next_training_data_batch (preprocessing.py:165-208) on a device-resident dataset in the reference's

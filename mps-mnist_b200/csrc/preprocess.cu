@@ -24,17 +24,25 @@ __device__ __forceinline__ int64_t wrap_row(int64_t start, int64_t t, int64_t to
   return r;
 }
 
-// four consecutive pixels as float32.  uint8: DataSet.__init__ of the TF-1.2 MNIST loader multiplies by 1/255 in float32
-__device__ __forceinline__ float4 load4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float4 load4(const uint8_t* p) {
-  const uchar4 q = __ldcs(reinterpret_cast<const uchar4*>(p));
-  const float k = (float)(1.0 / 255.0);
-  // __fmul_rn: the products must be rounded on their own (no contraction into the pooling adds) to match the loader
-  return make_float4(__fmul_rn((float)q.x, k), __fmul_rn((float)q.y, k), __fmul_rn((float)q.z, k), __fmul_rn((float)q.w, k));
-}
+// Raw pixel formats.  U8 follows DataSet.__init__ of the TF-1.2 MNIST loader (float32(u) * float32(1/255));
+// U8_DIV follows FashionMNISTpreprocessing.py:60 (u / 255.0 in float64, float32 when fed to the graph: the correctly
+// rounded quotient, which the float32 division gives for every u in 0..255 -- 126 of the 256 values differ from U8).
+struct U8Mul { uint8_t v; };
+struct U8Div { uint8_t v; };
+__device__ __forceinline__ float px(float v, const float*) { return v; }
+// __fmul_rn / __fdiv_rn: rounded on their own (no contraction into the pooling adds)
+__device__ __forceinline__ float px(uint8_t v, const U8Mul*) { return __fmul_rn((float)v, (float)(1.0 / 255.0)); }
+__device__ __forceinline__ float px(uint8_t v, const U8Div*) { return __fdiv_rn((float)v, 255.0f); }
 
+__device__ __forceinline__ float4 load4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p) {
+  const uchar4 q = __ldcs(reinterpret_cast<const uchar4*>(p));
+  return make_float4(px(q.x, p), px(q.y, p), px(q.z, p), px(q.w, p));
+}
 __device__ __forceinline__ float load1(const float* p) { return __ldcs(p); }
-__device__ __forceinline__ float load1(const uint8_t* p) { return __fmul_rn((float)__ldcs(p), (float)(1.0 / 255.0)); }
+template <typename T>
+__device__ __forceinline__ float load1(const T* p) { return px(__ldcs(reinterpret_cast<const uint8_t*>(p)), p); }
 
 // tile[s][i] (s = site inside the strip, i = image inside the tile, row pitch TI + 1) -> out, site-major.
 // A thread keeps its image and walks down the sites: one shared load, one store and a pointer bump per value.
@@ -60,9 +68,10 @@ __device__ __forceinline__ void write_sites(const float* tile, int nsites, int64
 // all the 16-byte loads of a pass before it touches the first result (UNROLL loads in flight per thread).
 constexpr int PRE_UNROLL = 8;
 
-// shrink = True: tf.nn.avg_pool(ksize 2x2, stride 2) then reshape to [rows/2 * cols/2] (MNISTpreprocessing.py:44-48).
+// shrink: tf.nn.avg_pool(ksize 2x2, stride 2) then reshape to [rows/2 * cols/2] (MNISTpreprocessing.py:44-48), or the
+// 2x2 block maximum of the Fashion-MNIST datasource (MAXP).
 // strip = pooled image row: the two raw rows under it (2*cols consecutive pixels) of 128 images.
-template <typename T>
+template <typename T, bool MAXP>
 __global__ void __launch_bounds__(256) preprocess_pool_kernel(const T* __restrict__ images, int64_t total, int rows, int cols,
                                                               int64_t start, int64_t B, int out_map, float* __restrict__ out) {
   __shared__ float tile[(PRE_MAXCOLS / 2) * PRE_LD];
@@ -87,8 +96,13 @@ __global__ void __launch_bounds__(256) preprocess_pool_kernel(const T* __restric
     for (int u = 0; u < U; ++u) {
       const int idx = base + u * 256, i = idx / Q, q = idx - i * Q;
       if (idx < n_items && i < n_img) {
-        tile[(2 * q) * PRE_LD + i] = ((a[u].x + a[u].y) + (b[u].x + b[u].y)) * 0.25f;
-        tile[(2 * q + 1) * PRE_LD + i] = ((a[u].z + a[u].w) + (b[u].z + b[u].w)) * 0.25f;
+        if (MAXP) {      // skimage.measure.block_reduce(image, (2, 2), np.max), FashionMNISTpreprocessing.py:61-65
+          tile[(2 * q) * PRE_LD + i] = fmaxf(fmaxf(a[u].x, a[u].y), fmaxf(b[u].x, b[u].y));
+          tile[(2 * q + 1) * PRE_LD + i] = fmaxf(fmaxf(a[u].z, a[u].w), fmaxf(b[u].z, b[u].w));
+        } else {
+          tile[(2 * q) * PRE_LD + i] = ((a[u].x + a[u].y) + (b[u].x + b[u].y)) * 0.25f;
+          tile[(2 * q + 1) * PRE_LD + i] = ((a[u].z + a[u].w) + (b[u].z + b[u].w)) * 0.25f;
+        }
       }
     }
   }
@@ -250,32 +264,38 @@ void set_flat_variant(int v) { g_flat_variant = v; }
 
 using namespace trmps;
 
-extern "C" int trmps_preprocess_batch(const void* images, int32_t dtype, int64_t total, int32_t rows, int32_t cols, int32_t shrink,
+namespace {
+
+template <typename T>
+int preprocess_typed(const T* images, int64_t total, int rows, int cols, int pool, int64_t start, int64_t B, int out_map, float* out,
+                     cudaStream_t st) {
+  if (pool == TRMPS_POOL_NONE)
+    return launch_flat<T, 1>(images, total, (int64_t)rows * cols, start, B, out_map, out, st, "trmps_preprocess_batch");
+  if (rows % 2 || cols % 4 || cols > PRE_MAXCOLS)
+    return bad("trmps_preprocess_batch: pooling needs an even number of rows and cols a multiple of 4, at most 64");
+  const int64_t tiles = ceil_div64(B, PRE_TI);
+  if (tiles * (rows / 2) > 0x7fffffff) return bad("trmps_preprocess_batch: batch too large");
+  const unsigned grid = (unsigned)(tiles * (rows / 2));
+  if (pool == TRMPS_POOL_AVG) preprocess_pool_kernel<T, false><<<grid, 256, 0, st>>>(images, total, rows, cols, start, B, out_map, out);
+  else preprocess_pool_kernel<T, true><<<grid, 256, 0, st>>>(images, total, rows, cols, start, B, out_map, out);
+  TRMPS_LAUNCH_OK("preprocess_pool_kernel");
+  return TRMPS_OK;
+}
+
+}  // namespace
+
+extern "C" int trmps_preprocess_batch(const void* images, int32_t dtype, int64_t total, int32_t rows, int32_t cols, int32_t pool,
                                       int64_t start, int64_t B, int32_t out_map, float* out, void* stream) {
   if (!images || !out || total <= 0 || rows <= 0 || cols <= 0 || start < 0 || start >= total || B < 0)
     return bad("trmps_preprocess_batch: bad argument (need 0 <= start < total, B >= 0)");
-  if (dtype != TRMPS_DT_F32 && dtype != TRMPS_DT_U8) return bad("trmps_preprocess_batch: dtype must be TRMPS_DT_F32 or TRMPS_DT_U8");
+  if (dtype < TRMPS_DT_F32 || dtype > TRMPS_DT_U8_DIV) return bad("trmps_preprocess_batch: dtype must be one of TRMPS_DT_*");
+  if (pool < TRMPS_POOL_NONE || pool > TRMPS_POOL_MAX) return bad("trmps_preprocess_batch: pool must be one of TRMPS_POOL_*");
   if (out_map < TRMPS_FM_PRECOMPUTED || out_map > TRMPS_FM_COS_SIN) return bad("trmps_preprocess_batch: unknown feature map");
   if (B == 0) return TRMPS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t tiles = ceil_div64(B, PRE_TI);
-  if (shrink) {
-    if (rows % 2 || cols % 4 || cols > PRE_MAXCOLS)
-      return bad("trmps_preprocess_batch: shrink needs an even number of rows and cols a multiple of 4, at most 64");
-    if (tiles * (rows / 2) > 0x7fffffff) return bad("trmps_preprocess_batch: batch too large");
-    const unsigned grid = (unsigned)(tiles * (rows / 2));
-    if (dtype == TRMPS_DT_F32)
-      preprocess_pool_kernel<float><<<grid, 256, 0, st>>>((const float*)images, total, rows, cols, start, B, out_map, out);
-    else
-      preprocess_pool_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)images, total, rows, cols, start, B, out_map, out);
-    TRMPS_LAUNCH_OK("preprocess_pool_kernel");
-  } else {
-    const int64_t len = (int64_t)rows * cols;
-    return dtype == TRMPS_DT_F32
-               ? launch_flat<float, 1>((const float*)images, total, len, start, B, out_map, out, st, "trmps_preprocess_batch")
-               : launch_flat<uint8_t, 1>((const uint8_t*)images, total, len, start, B, out_map, out, st, "trmps_preprocess_batch");
-  }
-  return TRMPS_OK;
+  if (dtype == TRMPS_DT_F32) return preprocess_typed((const float*)images, total, rows, cols, pool, start, B, out_map, out, st);
+  if (dtype == TRMPS_DT_U8) return preprocess_typed((const U8Mul*)images, total, rows, cols, pool, start, B, out_map, out, st);
+  return preprocess_typed((const U8Div*)images, total, rows, cols, pool, start, B, out_map, out, st);
 }
 
 extern "C" int trmps_batch_gather(const float* data, const float* labels, int64_t total, int32_t N, int32_t c, int32_t L,

@@ -12,4 +12,5 @@ from optimizers.parameterObjects import *
 from preprocessing.preprocessing import MPSDatasource
 from preprocessing.syntheticpreprocessing import SyntheticMNISTDatasource
 from preprocessing.MNISTpreprocessing import MNISTDatasource
+from preprocessing.FashionMNISTpreprocessing import FashionMNISTDatasource
 from trmps_native import FM_PRECOMPUTED, FM_ONE_SQRT3, FM_ONE_X, FM_COS_SIN

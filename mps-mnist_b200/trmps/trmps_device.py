@@ -84,10 +84,13 @@ def feature_layout(feature, N, d):
     raise ValueError("feature must be (N=%d, B, d=%d) phi or (N, B) pixels; got %r" % (N, d, shp))
 
 
-def preprocess_batch(images, rows, cols, shrink, start, batch, out_map=nat.FM_PRECOMPUTED, out=None):
+def preprocess_batch(images, rows, cols, shrink, start, batch, out_map=nat.FM_PRECOMPUTED, out=None, u8_divide=False):
     """Fused datasource preprocessing + batch fetch on the device (MNISTpreprocessing.py:44-55, preprocessing.py:165-208).
-    images: CUDA tensor (total, rows*cols), float32 in [0,1] or uint8.  Returns (N, batch) pooled pixels when
-    out_map == FM_PRECOMPUTED, else (N, batch, 2) phi of that map; the batch is images[(start + t) % total]."""
+    images: CUDA tensor (total, rows*cols), float32 in [0,1] or uint8 (scaled like the TF MNIST loader, or divided by 255
+    like FashionMNISTpreprocessing.py:60 when u8_divide).  shrink: False / True (2x2 average, MNIST) or a nat.POOL_* code
+    (POOL_MAX = the Fashion-MNIST datasource).  Returns (N, batch) pooled pixels when out_map == FM_PRECOMPUTED, else
+    (N, batch, 2) phi of that map; the batch is images[(start + t) % total]."""
+    pool = int(shrink)
     if not (isinstance(images, torch.Tensor) and images.is_cuda and images.is_contiguous()):
         raise ValueError("preprocess_batch: images must be a contiguous CUDA tensor")
     if images.dtype not in (torch.float32, torch.uint8):
@@ -95,16 +98,16 @@ def preprocess_batch(images, rows, cols, shrink, start, batch, out_map=nat.FM_PR
     total = images.shape[0]
     if images.numel() != total * rows * cols:
         raise ValueError("preprocess_batch: images must be (total, rows*cols)")
-    n_sites = (rows // 2) * (cols // 2) if shrink else rows * cols
+    n_sites = (rows // 2) * (cols // 2) if pool else rows * cols
     shape = (n_sites, batch) if out_map == nat.FM_PRECOMPUTED else (n_sites, batch, 2)
     if out is None:
         out = torch.empty(shape, dtype=torch.float32, device=images.device)
     elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
         raise ValueError("preprocess_batch: out must be a contiguous float32 tensor of shape %r" % (shape,))
-    dt = nat.DT_F32 if images.dtype == torch.float32 else nat.DT_U8
+    dt = nat.DT_F32 if images.dtype == torch.float32 else (nat.DT_U8_DIV if u8_divide else nat.DT_U8)
     if batch == 0:
         return out
-    nat.check(nat.load().trmps_preprocess_batch(images.data_ptr(), dt, total, rows, cols, int(bool(shrink)), int(start),
+    nat.check(nat.load().trmps_preprocess_batch(images.data_ptr(), dt, total, rows, cols, pool, int(start),
                                                 int(batch), int(out_map), out.data_ptr(), _stream_ptr()),
               "trmps_preprocess_batch")
     return out

@@ -13,7 +13,8 @@ LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libtrmps_b200.so")
 OK = 0
 FM_PRECOMPUTED, FM_ONE_SQRT3, FM_ONE_X, FM_COS_SIN = 0, 1, 2, 3
 LOSS_SOFTMAX_XENT, LOSS_SQUARED = 0, 1
-DT_F32, DT_U8 = 0, 1
+DT_F32, DT_U8, DT_U8_DIV = 0, 1, 2
+POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
 S_COST0, S_GDC, S_LR_STAR, S_COST1, S_LR, S_COUNT = 0, 1, 2, 3, 4, 32
 I_ACCEPT, I_TRIALS, I_M, I_SVD_SWEEPS, I_N_REVERT, I_N_EXHAUST, I_N_UPDATES, I_N_SWEEPS = 0, 1, 2, 3, 4, 5, 6, 7
 I_COUNT = 96

@@ -127,8 +127,50 @@ def run_preprocess_case(seed=21, count=26, size=40):
     return rec
 
 
+def write_idx(dirname, name, payload, dims, magic):
+    import gzip
+    header = magic.to_bytes(4, "big") + b"".join(int(x).to_bytes(4, "big") for x in dims)
+    with gzip.open(os.path.join(dirname, name), "wb") as fh:
+        fh.write(header + payload.tobytes())
+
+
+def run_fashion_case(seed=23, count=24):
+    """The reference's own FashionMNISTDatasource._load_with_correct_shape (FashionMNISTpreprocessing.py:56-77), shrink on
+    and off, on seeded idx files in a scratch directory (it reads '<ClassName>/train-images-idx3-ubyte.gz')."""
+    import tempfile
+    from preprocessing.FashionMNISTpreprocessing import FashionMNISTDatasource, data_type      # reference code
+    rng = np.random.default_rng(seed)
+    images = rng.integers(0, 256, (count, 784), dtype=np.uint8)
+    images[0, :56] = np.arange(56) * 4                    # every residue class of u / 255 rounding shows up
+    labels = rng.integers(0, 10, count).astype(np.uint8)
+    labels[0] = 9
+    rec = dict(images_u8=images, labels_u8=labels)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            os.mkdir("FashionMNISTDatasource")
+            write_idx("FashionMNISTDatasource", "train-images-idx3-ubyte.gz", images, (count, 28, 28), 2051)
+            write_idx("FashionMNISTDatasource", "train-labels-idx1-ubyte.gz", labels, (count,), 2049)
+            for shrink in (True, False):
+                ds = FashionMNISTDatasource.__new__(FashionMNISTDatasource)        # only the loader is exercised
+                ds.shrink = shrink
+                data, lab = ds._load_with_correct_shape(data_type.training)
+                assert data.dtype == np.float64 and np.all(data[..., 0] == 1)
+                rec["phi1_shrink" if shrink else "phi1_full"] = data[..., 1].astype(np.float32)   # what the float32 graph is fed
+                rec["labels_out"] = lab
+        finally:
+            os.chdir(cwd)
+    return rec
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        rec = run_fashion_case()
+    np.savez_compressed(os.path.join(OUT, "ref_fashion.npz"), **rec)
+    print("ref_fashion", rec["phi1_shrink"].shape, rec["phi1_full"].shape, rec["labels_out"].shape)
     sink = io.StringIO()
     with contextlib.redirect_stdout(sink):
         rec = run_preprocess_case()

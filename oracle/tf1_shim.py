@@ -427,6 +427,19 @@ def install():
         sys.modules[name] = types.ModuleType(name)
     sys.modules["tensorflow.examples.tutorials.mnist"].input_data = types.SimpleNamespace(read_data_sets=_NotAvailable)
     try:
+        import skimage.measure  # noqa: F401
+    except Exception:
+        # FashionMNISTpreprocessing.py:9 imports skimage for one call: block_reduce(image, (2, 2), np.max)
+        def block_reduce(image, block_size, func=np.sum, cval=0):
+            (bh, bw), (h, w) = block_size, image.shape
+            if h % bh or w % bw:
+                raise NotImplementedError("tf1_shim block_reduce: extents must be multiples of the block")
+            return func(image.reshape(h // bh, bh, w // bw, bw), axis=(1, 3))
+        sk = types.ModuleType("skimage")
+        sk.measure = types.ModuleType("skimage.measure")
+        sk.measure.block_reduce = block_reduce
+        sys.modules["skimage"], sys.modules["skimage.measure"] = sk, sk.measure
+    try:
         import matplotlib.pyplot  # noqa: F401
     except Exception:
         mpl = types.ModuleType("matplotlib")

@@ -69,6 +69,21 @@ def avg_pool_2x2(images, rows, cols):
     return ((top + bottom) * np.float32(0.25)).reshape(x.shape[0], -1)
 
 
+def max_pool_2x2(images, rows, cols):
+    """skimage.measure.block_reduce(image, (2, 2), np.max) per image, then flattened (FashionMNISTpreprocessing.py:61-68)."""
+    x = np.asarray(images).reshape(-1, rows // 2, 2, cols // 2, 2)
+    return x.max(axis=(2, 4)).reshape(x.shape[0], -1)
+
+
+def preprocess_fashion(images_u8, rows, cols, shrink):
+    """FashionMNISTDatasource._load_with_correct_shape (FashionMNISTpreprocessing.py:56-77): u8 / 255.0 in float64,
+    optional 2x2 maximum, phi = [1, x].  (B, rows*cols) uint8 -> (B, N, 2) float64, as the reference stores it."""
+    x = np.asarray(images_u8).reshape(len(images_u8), rows * cols) / 255.0
+    if shrink:
+        x = max_pool_2x2(x, rows, cols)
+    return np.stack([np.ones_like(x), x], axis=-1)
+
+
 def feature_map_f32(x, kind):
     """The feature maps evaluated the way a float32 TF graph does (constants cast to float32 first):
     MNISTpreprocessing.py:55, FashionMNISTpreprocessing.py:73.  (...,) -> (..., 2)."""

@@ -39,6 +39,58 @@ def test_matches_the_reference_codes_own_output():
         assert np.array_equal(got[..., 1].T, g[key])                 # bit-exact, including the wrapped-around samples
 
 
+def test_fashion_matches_the_reference_codes_own_output():
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "ref_fashion.npz"))
+    d = torch.from_numpy(g["images_u8"]).cuda()
+    n = len(g["images_u8"])
+    for pool, key in ((nat.POOL_MAX, "phi1_shrink"), (nat.POOL_NONE, "phi1_full")):
+        got = dev.preprocess_batch(d, 28, 28, pool, 0, n, out_map=nat.FM_ONE_X, u8_divide=True).cpu().numpy()
+        assert np.all(got[..., 0] == 1)
+        assert np.array_equal(got[..., 1].T, g[key])
+
+
+@pytest.mark.parametrize("kind", [o.FM_PRECOMPUTED, o.FM_ONE_X])
+@pytest.mark.parametrize("pool", [nat.POOL_MAX, nat.POOL_NONE])
+def test_fashion_pipeline_matches_oracle(pool, kind):
+    total, start, B = 257, 100, 700
+    u8 = seeded_images(total, seed=13)
+    got = dev.preprocess_batch(torch.from_numpy(u8).cuda(), 28, 28, pool, start, B, out_map=kind, u8_divide=True).cpu().numpy()
+    phi = o.preprocess_fashion(u8, 28, 28, pool == nat.POOL_MAX).astype(np.float32)
+    data = phi[..., 1] if kind == o.FM_PRECOMPUTED else phi
+    want, _, _ = o.next_batch(data, np.zeros((total, 1)), start, B)
+    assert np.array_equal(got, want)
+    f32 = (u8 / 255.0).astype(np.float32)                            # float32 input takes the same pooling path
+    got32 = dev.preprocess_batch(torch.from_numpy(f32).cuda(), 28, 28, pool, start, B, out_map=kind).cpu().numpy()
+    assert np.array_equal(got32, want)
+
+
+@pytest.mark.parametrize("shrink", [True, False])
+def test_fashion_datasource_from_idx_files(tmp_path, monkeypatch, shrink):
+    from trmps import FashionMNISTDatasource
+    monkeypatch.chdir(tmp_path)
+    os.mkdir("FashionMNISTDatasource")
+    rng = np.random.default_rng(8)
+    n_train, n_test = 300, 90
+    tr, te = seeded_images(n_train, seed=16), seeded_images(n_test, seed=17)
+    trl, tel = rng.integers(0, 10, n_train).astype(np.uint8), rng.integers(0, 10, n_test).astype(np.uint8)
+    trl[0] = tel[0] = 9
+    for name, arr, dims, magic in (("train-images-idx3-ubyte.gz", tr, (n_train, 28, 28), 2051), ("train-labels-idx1-ubyte.gz", trl, (n_train,), 2049),
+                                   ("t10k-images-idx3-ubyte.gz", te, (n_test, 28, 28), 2051), ("t10k-labels-idx1-ubyte.gz", tel, (n_test,), 2049)):
+        write_idx("FashionMNISTDatasource", name, arr, dims, magic)
+    ds = FashionMNISTDatasource(shrink=shrink)
+    data, labels = ds._training_data
+    assert np.array_equal(data, o.preprocess_fashion(tr, 28, 28, shrink).astype(np.float32))
+    assert labels.dtype.kind == "i" and np.array_equal(labels.argmax(1), trl)
+    assert np.array_equal(ds._test_data[0], o.preprocess_fashion(te, 28, 28, shrink).astype(np.float32))
+    feat, lab = ds.next_training_data_batch(64)
+    assert feat.shape == ((196 if shrink else 784), 64, 2)
+    os.remove(os.path.join("FashionMNISTDatasource", "train-images-idx3-ubyte.gz"))
+    assert np.array_equal(FashionMNISTDatasource(shrink=shrink)._training_data[0], data)      # from the .npy cache
+    os.remove(os.path.join("FashionMNISTDatasource", "training_data.npy"))
+    with pytest.raises(Exception, match="Please place the MNIST Data"):
+        FashionMNISTDatasource(shrink=shrink)
+
+
 @pytest.mark.parametrize("dtype", [np.uint8, np.float32])
 @pytest.mark.parametrize("shrink", [True, False])
 @pytest.mark.parametrize("kind", [o.FM_PRECOMPUTED, o.FM_ONE_SQRT3, o.FM_ONE_X, o.FM_COS_SIN])
@@ -90,6 +142,7 @@ def test_empty_batch_and_bad_arguments():
         (d.data_ptr(), nat.DT_U8, 8, 28, 30, 1, 0, 4, 0, out.data_ptr(), None),      # cols % 4 with shrink
         (d.data_ptr(), nat.DT_U8, 8, 27, 28, 1, 0, 4, 0, out.data_ptr(), None),      # odd rows with shrink
         (d.data_ptr(), nat.DT_U8, 8, 28, 28, 1, 0, 4, 9, out.data_ptr(), None),      # feature map
+        (d.data_ptr(), nat.DT_U8, 8, 28, 28, 3, 0, 4, 0, out.data_ptr(), None),      # pool code
         (None, nat.DT_U8, 8, 28, 28, 1, 0, 4, 0, out.data_ptr(), None),              # null images
     ]
     for args in bad:

@@ -11,7 +11,7 @@ import trmps_oracle as o
 ALL_NPZ = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 GOLDEN = [p for p in ALL_NPZ if not os.path.basename(p).startswith("ref_")]     # written by oracle/make_golden.py
 REF_GOLDEN = [p for p in ALL_NPZ if os.path.basename(p).startswith("ref_")      # written by the REFERENCE code under oracle/tf1_shim.py
-              and os.path.basename(p) != "ref_preprocess.npz"]                   # (sweep cases; the datasource case has its own test)
+              and os.path.basename(p) not in ("ref_preprocess.npz", "ref_fashion.npz")]   # (sweep cases; the datasource cases have their own tests)
 GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -215,3 +215,18 @@ def test_next_batch_oracle_follows_the_reference_datasource():
         want_f, want_l, start = o.next_batch(data, labels, start, batch)
         assert np.array_equal(got_f, want_f) and np.array_equal(got_l, want_l)
         assert ds.current_index % 23 == start
+
+
+def test_fashion_oracle_matches_reference_loader_code():
+    """o.preprocess_fashion against FashionMNISTDatasource._load_with_correct_shape of the reference
+    (FashionMNISTpreprocessing.py:56-77, run on seeded idx files): /255 in float64, 2x2 maximum, [1, x]."""
+    g = np.load(os.path.join(GOLDEN_DIR, "ref_fashion.npz"))
+    for shrink, key in ((True, "phi1_shrink"), (False, "phi1_full")):
+        phi = o.preprocess_fashion(g["images_u8"], 28, 28, shrink)
+        assert phi.dtype == np.float64 and np.all(phi[..., 0] == 1)
+        assert np.array_equal(phi[..., 1].astype(np.float32), g[key])
+    assert np.array_equal(g["labels_out"].argmax(1), g["labels_u8"])
+    # the float32 division the kernel uses is the same function of the byte as float64 division followed by the cast
+    u = np.arange(256)
+    assert np.array_equal((u / 255.0).astype(np.float32), u.astype(np.float32) / np.float32(255))
+    assert np.any((u / 255.0).astype(np.float32) != o.scale_uint8(u.astype(np.uint8)))       # and differs from the TF loader's
