@@ -18,6 +18,14 @@
 // (2^-2 .. 2^15: no overflow, error floor below 2^-23 of the row maximum) and the step is redone with the exact
 // exponent in the rare case it falls outside; the exponents are added back in fp32 only when the final environment is written.
 //
+// Order of accumulation.  The tensor core adds every MMA instruction's 16-term sum into the fp32 accumulator with
+// round-toward-zero, i.e. each instruction issued while the accumulator already has its final magnitude shrinks it by
+// half an ulp on average.  In a single contraction that is invisible (a few 1e-8); in a chain it compounds as a common
+// factor over the sites (measured: 1.4e-4 relative on the logits after 784 sites at KP=32 and after 196 sites at KP=128
+// with the main terms first, tests/test_gpu_fullsize.py).  The small products (l.h, h.l: 2^-11 of the result) are
+// therefore issued FIRST, while the accumulator is still small, and the h.h products last: KP/16 instructions round at
+// full magnitude instead of 3 KP/16.
+//
 // Shapes: KP = 32 / 64 / 128 (padded bond), TILES = 4 / 4 / 2 image tiles per CTA (TMEM columns 2*KP*TILES <= 512).
 // The tiles are staggered: while the tensor core works on one tile, the epilogue warpgroups of the others drain
 // TMEM and rebuild their A tiles.  Node images (pre-split fp16 hi/lo, built once per call, L2 resident) are
@@ -48,7 +56,7 @@ template <> struct ChainCfg<32> {
   static constexpr int PIECE_BYTES = 64 * 128;          // 64 rows (m,j), row = [hi(k 0..31) | lo(k 0..31)]
 };
 template <> struct ChainCfg<64> {
-  static constexpr int TILES = 4, WG = 1, NSTAGE = 4, PIECES = 2;  // pieces: hi, lo
+  static constexpr int TILES = 4, WG = 1, NSTAGE = 4, PIECES = 2;  // pieces: lo, hi
   static constexpr bool TILE_MAJOR = true;
   static constexpr int A_BYTES = 2 * 16384;             // [hi | lo] x one 64-wide k atom
   static constexpr int PIECE_BYTES = 128 * 128;
@@ -56,7 +64,7 @@ template <> struct ChainCfg<64> {
 template <> struct ChainCfg<128> {
   // N = 256 per MMA: M=128 MMAs with smaller N are bound by the shared-memory operand fetch (8 KB per 64 cycles),
   // at N = 256 the tensor pipe itself is the limit.  Two warpgroups per tile halve the epilogue latency.
-  static constexpr int TILES = 2, WG = 2, NSTAGE = 3, PIECES = 4;  // pieces: (ka0,hi) (ka0,lo) (ka1,hi) (ka1,lo)
+  static constexpr int TILES = 2, WG = 2, NSTAGE = 3, PIECES = 4;  // pieces: (ka0,lo) (ka1,lo) (ka0,hi) (ka1,hi)
   static constexpr bool TILE_MAJOR = false;
   static constexpr int A_BYTES = 4 * 16384;             // [hi ka0 | hi ka1 | lo ka0 | lo ka1]
   static constexpr int PIECE_BYTES = 256 * 128;
@@ -205,10 +213,10 @@ __global__ void chain_prep_kernel(const float* __restrict__ nodes, uint8_t* __re
     if (KP == 32) {          // one piece, row = [hi | lo]
       ph = base + k128_chunk_off(n, kc);
       pl = base + k128_chunk_off(n, 4 + kc);
-    } else {                 // pieces (ka, hi), (ka, lo)
+    } else {                 // pieces (lo, ka = 0..KA-1) then (hi, ka = 0..KA-1): the small products are issued first
       const int ka = kc >> 3, ch = kc & 7;
-      ph = base + (size_t)(2 * ka) * C::PIECE_BYTES + k128_chunk_off(n, ch);
-      pl = base + (size_t)(2 * ka + 1) * C::PIECE_BYTES + k128_chunk_off(n, ch);
+      ph = base + (size_t)(KP / 64 + ka) * C::PIECE_BYTES + k128_chunk_off(n, ch);
+      pl = base + (size_t)ka * C::PIECE_BYTES + k128_chunk_off(n, ch);
     }
     *reinterpret_cast<uint4*>(ph) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(pl) = *reinterpret_cast<const uint4*>(lo);
@@ -284,24 +292,23 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
         const uint32_t d = tmem_base + k * NCOL;
         const uint64_t ad = adesc0 + (uint64_t)(k * (C::A_BYTES >> 4));
         const uint64_t bd = bdesc0 + (uint64_t)(st * (C::PIECE_BYTES >> 4));
-        if (KP == 32) {
-          umma_f16(d, ad + 0, bd + 0, idesc, 0u);          // hi . hi
-          umma_f16(d, ad + 2, bd + 2, idesc, 1u);
-          umma_f16(d, ad + 4, bd + 0, idesc, 1u);          // lo . hi
+        if (KP == 32) {                                    // small terms first (see "Order of accumulation")
+          umma_f16(d, ad + 4, bd + 0, idesc, 0u);          // lo . hi
           umma_f16(d, ad + 6, bd + 2, idesc, 1u);
           umma_f16(d, ad + 0, bd + 4, idesc, 1u);          // hi . lo
           umma_f16(d, ad + 2, bd + 6, idesc, 1u);
+          umma_f16(d, ad + 0, bd + 0, idesc, 1u);          // hi . hi
+          umma_f16(d, ad + 2, bd + 2, idesc, 1u);
         } else {
           constexpr int KA = KP / 64;
-          const int ka = p >> 1;
+          const int ka = p < KA ? p : p - KA;
           const uint64_t ahi = ad + (uint64_t)(ka * 1024), alo = ad + (uint64_t)((KA + ka) * 1024);
-          if ((p & 1) == 0) {                              // piece holds g_hi: a_hi . g_hi and a_lo . g_hi
+          if (p < KA) {                                    // piece holds g_lo of atom ka: a_hi . g_lo
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_f16(d, ahi + 2 * ks, bd + 2 * ks, idesc, (p > 0 || ks > 0) ? 1u : 0u);
-              umma_f16(d, alo + 2 * ks, bd + 2 * ks, idesc, 1u);
-            }
-          } else {                                         // piece holds g_lo: a_hi . g_lo
+            for (int ks = 0; ks < 4; ++ks) umma_f16(d, ahi + 2 * ks, bd + 2 * ks, idesc, (p > 0 || ks > 0) ? 1u : 0u);
+          } else {                                         // piece holds g_hi of atom ka: a_lo . g_hi, then a_hi . g_hi
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_f16(d, alo + 2 * ks, bd + 2 * ks, idesc, 1u);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) umma_f16(d, ahi + 2 * ks, bd + 2 * ks, idesc, 1u);
           }

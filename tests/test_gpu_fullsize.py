@@ -1,0 +1,144 @@
+"""-m gpu tests at BASELINE.json's full sizes (cfg3: D=120, 60 000 images; cfg5: N=784, D=32, 1 M images).
+
+The oracle cannot walk a whole 60k-image sweep in seconds, so these cases use what is independent of the size:
+  * everything the path computes per image (environments, logits) is checked on a random sample of the images against
+    the fp64 oracle, and must not depend on which other images share the batch;
+  * what is summed over the batch (the gradient, the cost) is checked in full against fp64 matrix products, which NumPy
+    does in about a second at this size;
+  * exact power-of-two scaling of the weights scales the logits exactly;
+  * the full-size split (240 x 2400) is checked against LAPACK, with orthonormal a_j and a_j . a_j1 = rank-m truncation;
+  * the linearity the Armijo loop relies on, f(bond + lr delta) = f(bond) + lr f(delta).
+Tolerances: north_star's 1e-4 relative for logits, gradients and singular values; argmax exact on non-tied rows."""
+import numpy as np
+import pytest
+import torch
+
+import trmps_oracle as o
+import trmps_native as nat
+import trmps_device as dev
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def check_inference(N, D, B, sample, seed):
+    L, loc = 10, N // 2
+    device = torch.device("cuda", 0)
+    nodes = o.random_full_bond_mps(N, 2, L, D, loc=loc, seed=seed)
+    w = dev.DeviceWeights(nodes, loc, L, dev.bond_stride(nodes, loc, L), device)
+    gen = torch.Generator(device=device).manual_seed(seed)
+    pix = torch.rand((N, B), device=device, generator=gen)
+    logits = dev.predict(w, pix, nat.FM_COS_SIN)
+    assert bool(torch.isfinite(logits).all())
+    pick = torch.from_numpy(np.random.default_rng(seed).choice(B, sample, replace=False)).to(device)
+    sub = pix[:, pick].contiguous()
+    # (1) a random sample of the images against the fp64 oracle
+    phi64 = o.feature_map(sub.cpu().numpy().astype(np.float64), o.FM_COS_SIN, dtype=np.float64)
+    want = o.predict([n.astype(np.float64) for n in nodes], loc, phi64, L)
+    got = logits[pick].cpu().numpy()
+    assert rel(got, want) < RTOL
+    top2 = np.sort(want, axis=1)
+    clear = (top2[:, -1] - top2[:, -2]) > 1e-4 * np.abs(top2[:, -1])
+    assert clear.sum() > sample // 2
+    assert np.array_equal(got.argmax(1)[clear], want.argmax(1)[clear])
+    # (2) an image's logits do not depend on the rest of the batch
+    alone = dev.predict(w, sub, nat.FM_COS_SIN).cpu().numpy()
+    assert rel(alone, got) < 2e-6
+    # (3) exact power-of-two scaling of the special node scales every logit exactly
+    scaled = [n if i != loc else n * np.float32(4) for i, n in enumerate(nodes)]
+    w4 = dev.DeviceWeights(scaled, loc, L, w.Ds, device)
+    assert torch.equal(dev.predict(w4, sub, nat.FM_COS_SIN), 4 * torch.from_numpy(alone).to(device))
+
+
+def test_cfg5_inference_one_million_images():
+    check_inference(784, 32, 1000000, 192, seed=5)
+
+
+def test_cfg3_inference_sixty_thousand_images():
+    check_inference(196, 120, 60000, 96, seed=6)
+
+
+@pytest.mark.parametrize("direction", [+1, -1])
+def test_cfg3_bond_update_pieces_at_full_size(direction):
+    """One bond of cfg3's size (D=120: bond matrix 240 x 2400, 60 000 images) on a short chain: forward, cost, gradient
+    and <G, delta> against fp64 matrix products over the whole batch; linearity of the forward; the split against LAPACK."""
+    N, B, L, D, loc = 5, 60000, 10, 120, 2
+    pix, lab = o.synthetic_batch(N, B, L, seed=70)
+    phi = o.feature_map(pix, o.FM_COS_SIN)
+    nodes = o.random_full_bond_mps(N, 2, L, D, loc=loc, seed=71)
+    Ds = dev.bond_stride(nodes, loc, L, D)
+    st = dev.SweepState(N, B, L, Ds, nat.FM_COS_SIN, nat.LOSS_SOFTMAX_XENT, torch.device("cuda", 0))
+    st.set_nodes(nodes, loc)
+    st.set_batch(pix, lab)
+    st.init_env(loc)
+    n64 = [n.astype(np.float64) for n in nodes]
+    phi64 = o.feature_map(pix.astype(np.float64), o.FM_COS_SIN, dtype=np.float64)
+    C1s, C2s = o.setup_environments(n64, loc, phi64, L)
+    if direction > 0:
+        bond = np.einsum('lmij,njk->lmnik', n64[loc], n64[loc + 1])
+        Cn, Cf, pn, pf = C1s[loc], C2s[loc + 1], phi64[loc], phi64[loc + 1]
+    else:
+        lib = nat.load()
+        nat.check(lib.trmps_env_step(st.feat[loc + 1].data_ptr(), nat.FM_COS_SIN, B, st.Ds, -1, st.envR[loc + 1].data_ptr(),
+                                     st.slots[loc + 1].data_ptr(), st.dims[loc + 2:].data_ptr(), st.envR[loc].data_ptr(), None), "env_step")
+        C2 = o.chain_left(C2s[loc + 1], phi64[loc + 1], n64[loc + 1])
+        bond = np.einsum('nkj,lmji->lmnik', n64[loc - 1], n64[loc])
+        Cn, Cf, pn, pf = C2, C1s[loc - 1], phi64[loc], phi64[loc - 1]
+    reg = 1e-3
+    opt = dev.make_opt(lr=1e-3, max_size=D, reg=reg, min_singular_value=0.0)
+    st.bond_merge(loc, direction)
+    st.bond_gradient(loc, direction, opt)          # forward, loss and gradient of the merged bond
+    torch.cuda.synchronize()
+    # ---- per-image quantity: logits of every image
+    f64 = o.forward_factored(bond, Cn, Cf, pn, pf)
+    f0 = st.logits0().cpu().numpy()
+    assert rel(f0, f64) < RTOL
+    # ---- batch sums: cost, gradient, <G, delta>/B
+    h64 = o.softmax(f64)
+    cost64 = o.cost_softmax_xent(f64, lab.astype(np.float64))
+    sc = st.scalars().cpu().numpy()
+    assert abs(sc[nat.S_COST0] - cost64) < 1e-5 * abs(cost64)
+    G64 = o.gradient_factored(lab - h64, Cn, Cf, pn, pf) - 2 * reg * bond
+    dn, df = bond.shape[3], bond.shape[4]
+    gotG = st.bond_tensor(st.grad_matrix()).cpu().numpy()[:, :, :, :dn, :df]
+    assert rel(gotG, G64) < RTOL
+    gdc = np.sum(G64 * G64) / B
+    assert abs(sc[nat.S_GDC] - gdc) < 1e-4 * gdc
+    # ---- the linearity the Armijo loop relies on (baseoptimizer.py:299-322 evaluates f(bond + lr delta) per trial)
+    st.bond_forward(loc, direction, 1)              # f(delta), delta = the gradient just computed
+    fd = st.logits_delta().cpu().numpy()
+    lr = 1e-3
+    f_sum = o.forward_factored(bond + lr * G64, Cn, Cf, pn, pf)
+    assert rel(f0 + np.float32(lr) * fd, f_sum) < RTOL
+    # ---- the split of the 240 x 2400 bond against LAPACK
+    st.bond_split(loc, direction, opt)
+    torch.cuda.synchronize()
+    iw = st.iwork.cpu().numpy()
+    m = int(iw[nat.I_M])
+    assert m == D
+    M = np.transpose(bond, (1, 3, 0, 2, 4)).reshape(2 * dn, -1)
+    s_ref = np.linalg.svd(M, compute_uv=False)
+    sv = st.singular_values().cpu().numpy()[:len(s_ref)]
+    big = s_ref > 1e-3 * s_ref[0]
+    assert np.max(np.abs(sv[big] - s_ref[big]) / s_ref[big]) < RTOL
+    U, s, Vt = np.linalg.svd(M, full_matrices=False)
+    want = ((U[:, :m] * s[:m]) @ Vt[:m]).reshape(2, dn, L, 2, df).transpose(2, 0, 3, 1, 4)      # rank-m truncation
+    dims = st.dims.cpu().numpy()
+    slots, special = st.slots.cpu().numpy(), st.special.cpu().numpy()
+    if direction > 0:
+        a_j, a_j1 = slots[loc][:, :dims[loc], :m], special[:, :, :m, :dims[loc + 2]]
+        assert dims[loc + 1] == m
+        got = np.einsum('miq,lnqk->lmnik', a_j, a_j1)
+        ortho = np.einsum('miq,mir->qr', a_j, a_j)
+    else:
+        a_j, a_j1 = slots[loc][:, :m, :dims[loc + 1]], special[:, :, :dims[loc - 1], :m]
+        assert dims[loc] == m
+        got = np.einsum('mqi,lnkq->lmnik', a_j, a_j1)
+        ortho = np.einsum('mqi,mri->qr', a_j, a_j)
+    assert rel(got, want) < RTOL
+    assert np.max(np.abs(ortho - np.eye(m))) < 3e-5
