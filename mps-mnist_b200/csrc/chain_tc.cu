@@ -591,6 +591,13 @@ int64_t chain_site_bytes(int Ds) {
 }  // namespace
 
 bool chain_tc_supported(int Ds) { return Ds <= 128 && Ds % 4 == 0; }
+// Expected relative shrink of the logits after `nsites` fused sites: the round-toward-zero accumulation of the KP/16
+// h.h instructions per site ("Order of accumulation" above).  Per-site figures measured on dense random chains
+// (tools/chain_accuracy.py: 4.0e-5 after 783 sites at KP=32, 6.0e-5 after 783 at KP=64, 7.4e-5 after 195 at KP=128).
+double chain_tc_bias_estimate(int Ds, int nsites) {
+  const double per_site = Ds <= 32 ? 5.2e-8 : Ds <= 64 ? 7.8e-8 : 3.8e-7;
+  return per_site * (nsites > 0 ? nsites : 0);
+}
 int chain_tc_debug(float* out64) { return cudaMemcpyFromSymbol(out64, g_chain_dbg, 64 * sizeof(float)) == cudaSuccess ? 0 : -1; }
 // scratch for the images of `nsteps` sites plus their exponents (in floats)
 int64_t chain_tc_image_floats(int Ds, int nsteps) {

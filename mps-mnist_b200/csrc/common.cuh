@@ -169,6 +169,7 @@ bool grad_h_supported(int64_t B, int Ds, int L);
 int launch_grad_h(const float* e_near, const float* e_far, const float* phi_near, const float* sres, float* gpart, int gsplit,
                   int64_t B, int Ds, int L, int32_t* scratch, float* out, cudaStream_t st);
 bool chain_tc_supported(int Ds);
+double chain_tc_bias_estimate(int Ds, int nsites);
 int chain_tc_debug(float* out64);
 int64_t chain_tc_image_floats(int Ds, int nsteps);
 int launch_chain_tc(const float* feat, int fm, int64_t B, int Ds, int L, const float* nodes, int first, int dir, int nsteps,

@@ -373,8 +373,13 @@ extern "C" int trmps_predict(const trmps_predict_desc* p, void* stream) {
   float* fpart = phi_loc + 2 * B;
   const size_t slot = (size_t)2 * Ds * Ds;
   int rc;
-  if (option_value(2) == 0 && chain_tc_supported(Ds)) {
-    // fused tensor-core chains: the environments never leave the SM between sites
+  // fused tensor-core chains unless their accumulated rounding bias would use up north_star's 1e-4 on the logits
+  // (only chains longer than the BASELINE configurations: > 1500 sites at D <= 32, > 1000 at D <= 64, > 230 at D <= 128);
+  // option 2 = 2 keeps them regardless
+  const bool chain_fused = chain_tc_supported(Ds) &&
+                           (option_value(2) == 2 || (option_value(2) == 0 && chain_tc_bias_estimate(Ds, N - 1) <= 9e-5));
+  if (chain_fused) {
+    // the environments never leave the SM between sites
     float* img = fpart + B * L;
     img += (256 - ((uintptr_t)img / sizeof(float)) % 256) % 256;      // bulk copies want 16-byte alignment; keep 1 KB
     if ((rc = launch_chain_tc(p->feat, fm, B, Ds, L, p->nodes, 0, +1, p->loc, 0, img, buf[0], st))) return rc;

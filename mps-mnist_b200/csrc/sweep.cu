@@ -462,7 +462,7 @@ extern "C" int64_t trmps_launch_count(void) { return (int64_t)g_launches; }
 extern "C" int trmps_set_option(int32_t option, int32_t value) {
   if (option == 0 && (value == 0 || value == 1 || value == 2)) { g_grad_impl = value; return TRMPS_OK; }
   if (option == 1 && (value == 0 || value == 1 || value == 2)) { g_fwd_impl = value; return TRMPS_OK; }
-  if (option == 2 && (value == 0 || value == 1)) { g_chain_impl = value; return TRMPS_OK; }
+  if (option == 2 && (value == 0 || value == 1 || value == 2)) { g_chain_impl = value; return TRMPS_OK; }
   if (option == 3 && value >= 0 && value <= 3) { set_flat_variant(value); return TRMPS_OK; }
   set_error("trmps_set_option: unknown option %d / value %d", option, value);
   return TRMPS_E_ARG;

@@ -142,3 +142,22 @@ def test_cfg3_bond_update_pieces_at_full_size(direction):
         ortho = np.einsum('mqi,mri->qr', a_j, a_j)
     assert rel(got, want) < RTOL
     assert np.max(np.abs(ortho - np.eye(m))) < 3e-5
+
+
+def test_long_wide_chain_keeps_the_tolerance():
+    """N=784 at D=120 is longer than any BASELINE configuration: the fused chain's round-toward-zero accumulation would
+    shrink the logits by ~2.4e-4 there, so trmps_predict takes the per-site FP32 path (trmps_set_option(2, 2) overrides)."""
+    N, D, B, L = 784, 120, 256, 10
+    loc = N // 2
+    nodes = o.random_full_bond_mps(N, 2, L, D, loc=loc, seed=9)
+    w = dev.DeviceWeights(nodes, loc, L, dev.bond_stride(nodes, loc, L), torch.device("cuda", 0))
+    pix = torch.rand((N, B), device="cuda", generator=torch.Generator(device="cuda").manual_seed(9))
+    phi64 = o.feature_map(pix.cpu().numpy().astype(np.float64), o.FM_COS_SIN, dtype=np.float64)
+    want = o.predict([n.astype(np.float64) for n in nodes], loc, phi64, L)
+    assert rel(dev.predict(w, pix, nat.FM_COS_SIN).cpu().numpy(), want) < RTOL
+    try:
+        nat.set_option(nat.OPT_CHAIN_IMPL, nat.CHAIN_TCGEN05_ALWAYS)
+        forced = rel(dev.predict(w, pix, nat.FM_COS_SIN).cpu().numpy(), want)
+    finally:
+        nat.set_option(nat.OPT_CHAIN_IMPL, nat.CHAIN_TCGEN05)
+    assert 1e-4 < forced < 5e-4          # the documented bias; argmax is unaffected (a common factor)

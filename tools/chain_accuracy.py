@@ -15,7 +15,7 @@ for N, D, B in ((784, 32, 4096), (196, 120, 2048), (784, 64, 2048), (784, 120, 1
     phi64 = o.feature_map(sub.cpu().numpy().astype(np.float64), o.FM_COS_SIN, dtype=np.float64)
     want = o.predict([n.astype(np.float64) for n in nodes], loc, phi64, L)
     line = "N=%d D=%d:" % (N, D)
-    for name, impl in (("tcgen05 fp16-split chain", nat.CHAIN_TCGEN05), ("per-site FP32 SIMT", nat.CHAIN_SIMT)):
+    for name, impl in (("default", nat.CHAIN_TCGEN05), ("tcgen05 fp16-split chain (forced)", nat.CHAIN_TCGEN05_ALWAYS), ("per-site FP32 SIMT", nat.CHAIN_SIMT)):
         nat.set_option(nat.OPT_CHAIN_IMPL, impl)
         got = dev.predict(w, pix, nat.FM_COS_SIN)[:128].cpu().numpy().astype(np.float64)
         err = np.linalg.norm(got - want) / np.linalg.norm(want)
