@@ -161,3 +161,50 @@ def test_long_wide_chain_keeps_the_tolerance():
     finally:
         nat.set_option(nat.OPT_CHAIN_IMPL, nat.CHAIN_TCGEN05)
     assert 1e-4 < forced < 5e-4          # the documented bias; argmax is unaffected (a common factor)
+
+
+def test_cfg3_half_sweep_invariants():
+    """The benchmark's workload itself (N=196, D=120, 60 000 images, 195 bond updates left to right) and what must hold
+    after it, whatever the size: every node left behind is an isometry; the bond dimension is max_size wherever the rank allows it; the
+    updated MPS evaluated by the inference path (fused tensor-core chains) and by the training path (cached environments of
+    the sweep + the bond contraction) are the same function, and both match the fp64 oracle on a sample of the images."""
+    from bench import synthetic_pixels, full_bond_mps
+    N, D, L, B, loc = 196, 120, 10, 60000, 0
+    pix, lab = synthetic_pixels(N, B, L, seed=100)
+    nodes = full_bond_mps(N, 2, L, D, loc)
+    st = dev.SweepState(N, B, L, dev.bond_stride(nodes, loc, L, D), nat.FM_COS_SIN, nat.LOSS_SOFTMAX_XENT, torch.device("cuda", 0))
+    st.set_nodes(nodes, loc)
+    st.set_batch(pix, lab)
+    opt = dev.make_opt(lr=1e-4, max_size=D, reg=1e-3, min_singular_value=0.0)
+    st.init_env(loc)
+    st.sweep(loc, N - 1, +1, opt)
+    st.loc = N - 1
+    torch.cuda.synchronize()
+    iw = st.iwork.cpu().numpy()
+    assert int(iw[nat.I_N_UPDATES]) == N - 1
+    dims = st.dims.cpu().numpy()
+    want_dims = [2 * L]
+    for i in range(N - 1):
+        want_dims.append(min(D, 2 * want_dims[-1]))           # min_singular_value = 0: m = min(max_size, rank bound d * Dl)
+    assert dims[:N].tolist() == want_dims and dims[N] == 2 * L
+    new_nodes = st.get_nodes()
+    assert all(np.isfinite(w).all() for w in new_nodes)
+    worst = 0.0
+    for i in range(N - 1):                                   # a_j of every split: orthonormal columns (optimizer.py:303-306)
+        a = new_nodes[i].astype(np.float64)
+        g = np.einsum('miq,mir->qr', a, a)
+        worst = max(worst, float(np.max(np.abs(g - np.eye(g.shape[0])))))
+    assert worst < 5e-5
+    # the same function through both kernel families, against fp64 on a sample
+    sample = np.random.default_rng(3).choice(B, 48, replace=False)
+    phi64 = o.feature_map(pix[:, sample].astype(np.float64), o.FM_COS_SIN, dtype=np.float64)
+    want = o.predict([w.astype(np.float64) for w in new_nodes], N - 1, phi64, L)
+    inference = dev.predict(st.weights_view(), st.feat, nat.FM_COS_SIN).cpu().numpy()
+    assert rel(inference[sample], want) < RTOL
+    st.bond_merge(N - 1, -1)                                  # bond (N-2, N-1) from the swept nodes; C1s[N-2] is the sweep's own cache
+    st.bond_forward(N - 1, -1, 0)
+    training = st.logits0().cpu().numpy()
+    assert rel(training[sample], want) < RTOL
+    assert rel(training, inference) < 1.5e-4
+    agree = np.mean(training.argmax(1) == inference.argmax(1))
+    assert agree > 0.9995
