@@ -205,6 +205,15 @@ int trmps_preprocess_batch(const void* images, int32_t dtype, int64_t total, int
 int trmps_batch_gather(const float* data, const float* labels, int64_t total, int32_t N, int32_t c, int32_t L,
                        int64_t start, int64_t B, float* feat_out, float* labels_out, void* stream);
 
+/* MPS._lin_reg (mps.py:331-399): the linear pre-training that initialises the MPS -- `iterations` steps of plain gradient
+ * descent on a softmax regression (loss_kind SOFTMAX_XENT: mean cross-entropy, mps.py:327-329; SQUARED: 0.5 * sum of squares,
+ * squaredDistanceMPS.py:29-30) over phi[..., 1], zero initial model, minibatches of `batch` consecutive samples of a
+ * device-resident dataset in the reference's storage layout: data (total, N, 2), labels (total, L), rows
+ * (start + iteration * batch + t) % total.  All iterations run inside one launch.  weight: (N, L) row-major, bias: (L). */
+int trmps_linreg_pretrain(const float* data, const float* labels, int64_t total, int32_t N, int32_t L, int64_t start,
+                          int32_t iterations, int32_t batch, float learning_rate, int32_t loss_kind, float* weight,
+                          float* bias, void* stream);
+
 /* one environment step, _chain_multiply_r/_l (mps.py:500-519), _find_C1/_find_C2 (baseoptimizer.py:160-201).
  * dir=+1: out[t,j] = sum_{m,i} phi[t,m] in[t,i] node[m,i,j];  dir=-1: out[t,i] = sum_{m,j} phi[t,m] node[m,i,j] in[t,j].
  * feat_site points at this site's pixels (B) or phi (B,2). din = contracted bond dim. */

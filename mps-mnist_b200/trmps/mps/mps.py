@@ -75,24 +75,24 @@ class MPS(object):
             self._special_node_loc = self.input_size // 2
 
     def _lin_reg(self, data_source, iterations, learning_rate):
-        """Softmax-regression pre-training on phi[..., 1:] with 100-image minibatches (mps.py:331-399).
-        Plain gradient descent on the mean cross-entropy (squared error for sqMPS), zero init."""
-        n_in = self.input_size * (self.d_feature - 1)
-        use_cuda = torch.cuda.is_available()
-        tdev = torch.device('cuda') if use_cuda else torch.device('cpu')
-        W = torch.zeros((n_in, self.d_output), dtype=torch.float32, device=tdev)
-        b = torch.zeros((self.d_output,), dtype=torch.float32, device=tdev)
-        for _ in range(int(iterations)):
-            feat, lab = data_source.next_training_data_batch(100)
-            if not isinstance(feat, torch.Tensor):                  # device-resident datasources hand out CUDA tensors
-                feat, lab = np.ascontiguousarray(feat), np.asarray(lab)
-            x = torch.as_tensor(feat, dtype=torch.float32, device=tdev)[:, :, 1:]
-            x = x.permute(1, 0, 2).reshape(x.shape[1], n_in)
-            y = torch.as_tensor(lab, dtype=torch.float32, device=tdev)
-            z = x @ W + b
-            gz = self._lin_reg_grad(z, y)
-            W -= learning_rate * (x.t() @ gz)
-            b -= learning_rate * gz.sum(0)
+        """Softmax-regression pre-training on phi[..., 1:] with 100-image minibatches (mps.py:331-399): plain gradient
+        descent on the mean cross-entropy (squared error for sqMPS), zero init.  All iterations run inside one kernel
+        launch (trmps_linreg_pretrain) on the training set kept on the GPU; the datasource's read position ends where the
+        reference's `iterations` calls of next_training_data_batch(100) leave it."""
+        if self.d_feature != 2:
+            raise ValueError("this build has d_feature = 2 (SURVEY.md section 8)")
+        nat.require_gpu(torch.cuda.current_device())
+        resident = getattr(data_source, "_device_training", None)
+        if resident is None:
+            data, labels = data_source._training_data
+            tdev = torch.device('cuda', torch.cuda.current_device())
+            resident = (torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(tdev),
+                        torch.from_numpy(np.ascontiguousarray(labels, dtype=np.float32)).to(tdev))
+        total = resident[0].shape[0]
+        start = data_source.current_index % total
+        W, b = dev.linreg_pretrain(resident[0], resident[1], start, int(iterations), learning_rate, self.loss_kind, batch=100)
+        if iterations > 0:
+            data_source.current_index = (start + 100 * int(iterations)) % total or total
         # (n_in, L) -> (N, d-1, L), matching the reshapes at mps.py:358-361
         self.weight = W.t().reshape(self.d_output, self.input_size, self.d_feature - 1).permute(1, 2, 0).cpu().numpy()
         self.bias = b.cpu().numpy()
@@ -100,11 +100,6 @@ class MPS(object):
             site = int(np.unravel_index(self.weight.argmax(), self.weight.shape)[0])
             site = min(max(site, 1), self.input_size - 2)      # mps.py:392-399
             self._special_node_loc = site
-
-    @staticmethod
-    def _lin_reg_grad(z, y):
-        # d/dz of mean softmax cross-entropy (mps.py:327-329)
-        return (torch.softmax(z, dim=1) - y) / z.shape[0]
 
     def _setup_nodes(self):
         # mps.py:401-423

@@ -20,6 +20,5 @@ class sqMPS(MPS):
         f, y = _to_numpy(f).astype(np.float32), _to_numpy(labels).astype(np.float32)
         return np.float32(0.5 * np.mean(np.square(f - y)))     # squaredDistanceMPS.py:25-27
 
-    @staticmethod
-    def _lin_reg_grad(z, y):
-        return z - y                                            # d/dz of 0.5*sum((z-y)^2), squaredDistanceMPS.py:29-30
+    # the linear pre-training descends 0.5 * sum((z - y)^2) (squaredDistanceMPS.py:29-30): loss_kind selects it in
+    # trmps_linreg_pretrain

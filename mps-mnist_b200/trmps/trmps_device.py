@@ -141,6 +141,23 @@ def batch_gather(data, labels, start, batch, feat_out=None, labels_out=None):
     return feat_out, labels_out
 
 
+def linreg_pretrain(data, labels, start, iterations, learning_rate, loss_kind=nat.LOSS_SOFTMAX_XENT, batch=100):
+    """MPS._lin_reg (mps.py:331-399) on a device-resident dataset: data (total, N, 2) phi, labels (total, L), float32 CUDA.
+    Returns weight (N, L) and bias (L) after `iterations` minibatch steps starting at dataset row `start`."""
+    for name, x in (("data", data), ("labels", labels)):
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.is_contiguous() and x.dtype == torch.float32):
+            raise ValueError("linreg_pretrain: %s must be a contiguous float32 CUDA tensor" % name)
+    if data.dim() != 3 or data.shape[2] != 2 or labels.dim() != 2 or labels.shape[0] != data.shape[0]:
+        raise ValueError("linreg_pretrain: data must be (total, N, 2) and labels (total, L)")
+    total, N, L = data.shape[0], data.shape[1], labels.shape[1]
+    weight = torch.empty((N, L), dtype=torch.float32, device=data.device)
+    bias = torch.empty((L,), dtype=torch.float32, device=data.device)
+    nat.check(nat.load().trmps_linreg_pretrain(data.data_ptr(), labels.data_ptr(), total, N, L, int(start) % total, int(iterations),
+                                               int(batch), float(learning_rate), int(loss_kind), weight.data_ptr(),
+                                               bias.data_ptr(), _stream_ptr()), "trmps_linreg_pretrain")
+    return weight, bias
+
+
 class DeviceWeights(object):
     """MPS weights resident on the GPU in slot layout."""
 

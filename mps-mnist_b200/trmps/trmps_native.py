@@ -70,6 +70,8 @@ _SIGNATURES = {
                                          C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "trmps_batch_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "trmps_linreg_pretrain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
+                                        C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "trmps_env_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "trmps_predict": (C.c_int, [C.POINTER(PredictDesc), C.c_void_p]),

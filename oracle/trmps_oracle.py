@@ -112,6 +112,26 @@ def next_batch(data, labels, start, batch_size):
     return np.swapaxes(data[rows], 0, 1), labels[rows], int((start + batch_size) % total)
 
 
+def lin_reg(data, labels, start, iterations, learning_rate, loss_kind=SOFTMAX_XENT, batch=100, dtype=np.float64):
+    """MPS._lin_reg (mps.py:331-399): gradient descent from zero on z = x W + b with x = phi[..., 1] (mps.py:345-349),
+    cost = mean softmax cross-entropy (mps.py:327-329) or 0.5 * sum of squares (squaredDistanceMPS.py:29-30), one minibatch
+    of `batch` consecutive samples per iteration (next_training_data_batch(100), wrapping).  data (total, N, 2), labels
+    (total, L).  Returns weight (N, L), bias (L) and the next read position.  TensorFlow's autodiff is restated as the
+    closed-form gradient; the reference code itself cannot run under the shim here (it needs tf.train)."""
+    data, labels = np.asarray(data, dtype=dtype), np.asarray(labels, dtype=dtype)
+    total, N = data.shape[0], data.shape[1]
+    W, b = np.zeros((N, labels.shape[1]), dtype=dtype), np.zeros(labels.shape[1], dtype=dtype)
+    lr = dtype(learning_rate)
+    for it in range(iterations):
+        rows = (start + it * batch + np.arange(batch)) % total
+        x, y = data[rows, :, 1], labels[rows]
+        z = x @ W + b
+        g = (z - y) if loss_kind == SQUARED else (softmax(z) - y) / dtype(batch)
+        W -= lr * (x.T @ g)
+        b -= lr * g.sum(axis=0)
+    return W, b, int((start + iterations * batch) % total)
+
+
 # --------------------------------------------------------------------------- initial MPS
 def start_vector(L, dtype=np.float32):
     """trmps/mps/mps.py:446-454  [0_L, 1_L]"""

@@ -216,3 +216,54 @@ def test_mnist_datasource_from_idx_files(tmp_path, monkeypatch, shrink):
     assert np.array_equal(again._training_data[0], data)
     with pytest.raises(FileNotFoundError):
         MNISTDatasource(shrink=not shrink, data_dir="nowhere")
+
+
+# --------------------------------------------------------------------------------------------- linear pre-training
+@pytest.mark.parametrize("loss", [o.SOFTMAX_XENT, o.SQUARED])
+@pytest.mark.parametrize("N,total,start,iters", [(20, 230, 0, 57), (196, 1000, 950, 200), (784, 400, 3, 40), (300, 128, 100, 25)])
+def test_linreg_pretrain_matches_oracle(loss, N, total, start, iters):
+    """trmps_linreg_pretrain (all iterations in one launch) against the oracle restatement of MPS._lin_reg
+    (mps.py:331-399) in fp64, with minibatches that wrap around the dataset and chains longer than one 256-site chunk."""
+    rng = np.random.default_rng(N + iters)
+    L = 10
+    cls = rng.integers(0, L, total)
+    pix = rng.random((total, N), dtype=np.float32)
+    pix[np.arange(total), cls % N] += 1.0                              # something to learn
+    data = o.feature_map_f32(pix, o.FM_ONE_SQRT3)                      # (total, N, 2)
+    labels = np.eye(L, dtype=np.float32)[cls]
+    lr = 0.05 if loss == o.SOFTMAX_XENT else 2e-4
+    W, b = dev.linreg_pretrain(torch.from_numpy(data).cuda(), torch.from_numpy(labels).cuda(), start, iters, lr, loss)
+    wantW, wantb, _ = o.lin_reg(data, labels, start, iters, lr, loss)
+    assert np.isfinite(wantW).all() and np.abs(wantW).max() > 1e-3
+    assert rel(W.cpu().numpy(), wantW) < 1e-4 and rel(b.cpu().numpy(), wantb) < 1e-4
+    W32, b32, _ = o.lin_reg(data, labels, start, iters, lr, loss, dtype=np.float32)
+    assert rel(W.cpu().numpy(), wantW) < max(20 * rel(W32, wantW), 2e-6)       # no worse than fp32 NumPy
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def test_prepare_with_datasource_follows_the_reference_semantics():
+    """MPS.prepare(data_source): zero iterations leave a zero model; the read position of the datasource advances by
+    100 * iterations like the reference's loop; the special node location comes from the largest weight (mps.py:390-399)."""
+    from trmps import MPS, sqMPS, SyntheticMNISTDatasource
+    ds = SyntheticMNISTDatasource(shrink=True, n_train=730, n_test=50, seed=3)
+    net = MPS(2, 10, 196)
+    net.prepare(ds, iterations=37, learning_rate=0.05)
+    assert ds.current_index == (37 * 100) % 730
+    data, labels = ds._training_data
+    W, b, _ = o.lin_reg(data, labels, 0, 37, 0.05)
+    assert rel(net.weight[:, 0, :], W) < 1e-4 and rel(net.bias, b) < 1e-4
+    site = int(np.unravel_index(net.weight.argmax(), net.weight.shape)[0])
+    assert net._special_node_loc == min(max(site, 1), 194)
+    # continuing from the advanced read position, on a device-resident datasource, squared loss
+    ds.to_device()
+    sq = sqMPS(2, 10, 196)
+    sq.prepare(ds, iterations=5, learning_rate=1e-4)
+    W2, b2, nxt = o.lin_reg(data, labels, (37 * 100) % 730, 5, 1e-4, o.SQUARED)
+    assert rel(sq.weight[:, 0, :], W2) < 1e-4 and ds.current_index == nxt
+    zero = MPS(2, 10, 196)
+    zero.prepare(ds, iterations=0)
+    assert not zero.weight.any() and not zero.bias.any()
