@@ -64,10 +64,12 @@ def test_cfg3_inference_sixty_thousand_images():
 
 
 @pytest.mark.parametrize("direction", [+1, -1])
-def test_cfg3_bond_update_pieces_at_full_size(direction):
-    """One bond of cfg3's size (D=120: bond matrix 240 x 2400, 60 000 images) on a short chain: forward, cost, gradient
-    and <G, delta> against fp64 matrix products over the whole batch; linearity of the forward; the split against LAPACK."""
-    N, B, L, D, loc = 5, 60000, 10, 120, 2
+@pytest.mark.parametrize("D,B", [(120, 60000), (64, 60000), (20, 20000)], ids=["cfg3", "cfg4", "cfg2"])
+def test_bond_update_pieces_at_full_size(direction, D, B):
+    """One bond at the bond dimension and batch of cfg3 (D=120: bond matrix 240 x 2400, 60 000 images), cfg4 (D=64) and
+    cfg2 (D=20, 20 000 images) on a short chain: forward, cost, gradient and <G, delta> against fp64 matrix products over
+    the whole batch; linearity of the forward; the split against LAPACK."""
+    N, L, loc = 5, 10, 2
     pix, lab = o.synthetic_batch(N, B, L, seed=70)
     phi = o.feature_map(pix, o.FM_COS_SIN)
     nodes = o.random_full_bond_mps(N, 2, L, D, loc=loc, seed=71)
