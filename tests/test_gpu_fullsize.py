@@ -210,3 +210,56 @@ def test_cfg3_half_sweep_invariants():
     assert rel(training, inference) < 1.5e-4
     agree = np.mean(training.argmax(1) == inference.argmax(1))
     assert agree > 0.9995
+
+
+def test_cfg3_single_site_update_at_full_size():
+    """One single-site update (singlesiteOptimizer.py:49-138) at cfg3's bond dimension with all 60 000 images: cost and
+    <G, delta> against fp64 matrix products over the whole batch, the singular values of the updated node against LAPACK,
+    and the function the two touched sites represent afterwards against the rank-m truncation."""
+    N, B, L, D, loc = 5, 60000, 10, 120, 2
+    pix, lab = o.synthetic_batch(N, B, L, seed=80)
+    nodes = o.random_full_bond_mps(N, 2, L, D, loc=loc, seed=81)
+    st = dev.SweepState(N, B, L, dev.bond_stride(nodes, loc, L, D), nat.FM_COS_SIN, nat.LOSS_SOFTMAX_XENT, torch.device("cuda", 0))
+    st.set_nodes(nodes, loc)
+    st.set_batch(pix, lab)
+    reg, lr = 1e-3, 1e-4
+    opt = dev.make_opt(lr=lr, max_size=D, reg=reg, min_singular_value=0.0, single_site=True)
+    st.init_env(loc)
+    st.bond_step(loc, +1, opt)
+    torch.cuda.synchronize()
+    n64 = [n.astype(np.float64) for n in nodes]
+    phi64 = o.feature_map(pix.astype(np.float64), o.FM_COS_SIN, dtype=np.float64)
+    C1s, C2s = o.setup_environments_single(n64, loc, phi64, L)
+    S = n64[loc]                                                                   # (L, d, Dl, Dr)
+    Dl, Dr = S.shape[2], S.shape[3]
+    P = (phi64[loc][:, :, None] * C1s[loc][:, None, :]).reshape(B, 2 * Dl)       # [t, (m, i)]
+    Smat = np.transpose(S, (1, 2, 0, 3)).reshape(2 * Dl, L * Dr)                   # rows (m, i), columns (l, k)
+    C2 = C2s[loc]
+    f = np.einsum('tlk,tk->tl', (P @ Smat).reshape(B, L, Dr), C2)
+    y = lab.astype(np.float64)
+    cost0 = o.cost_softmax_xent(f, y)
+    W = ((y - o.softmax(f))[:, :, None] * C2[:, None, :]).reshape(B, L * Dr)
+    G = P.T @ W - 2 * reg * Smat
+    sc, iw = st.scalars().cpu().numpy(), st.iwork.cpu().numpy()
+    assert abs(sc[nat.S_COST0] - cost0) < 1e-5 * abs(cost0)
+    gdc = np.sum(G * G) / B
+    assert abs(sc[nat.S_GDC] - gdc) < 1e-4 * gdc
+    lr_star = float(sc[nat.S_LR_STAR])
+    assert (lr_star > 0) == bool(iw[nat.I_ACCEPT])
+    M = Smat + lr_star * G                                                        # the node the split saw
+    U, s, Vt = np.linalg.svd(M, full_matrices=False)
+    m = int(iw[nat.I_M])
+    assert m == D
+    sv = st.singular_values().cpu().numpy()[:len(s)]
+    big = s > 1e-3 * s[0]
+    assert np.max(np.abs(sv[big] - s[big]) / s[big]) < RTOL
+    # isometry left at `loc`, S V absorbed by node loc + 1 (singlesiteOptimizer.py:124-125): compare the two-site product
+    want_aj1 = ((s[:m, None] * Vt[:m]).reshape(m, L, Dr))                          # (q, l, k)
+    want = np.einsum('miq,qlk,nkj->lmnij', U[:, :m].reshape(2, Dl, m), want_aj1, n64[loc + 1])
+    dims = st.dims.cpu().numpy()
+    slots, special = st.slots.cpu().numpy(), st.special.cpu().numpy()
+    a_j = slots[loc][:, :dims[loc], :m]
+    new_special = special[:, :, :m, :dims[loc + 2]]                               # (l, n, q, j)
+    got = np.einsum('miq,lnqj->lmnij', a_j, new_special)
+    assert rel(got, want) < RTOL
+    assert np.max(np.abs(np.einsum('miq,mir->qr', a_j, a_j) - np.eye(m))) < 3e-5
