@@ -263,3 +263,40 @@ def test_cfg3_single_site_update_at_full_size():
     got = np.einsum('miq,lnqj->lmnij', a_j, new_special)
     assert rel(got, want) < RTOL
     assert np.max(np.abs(np.einsum('miq,mir->qr', a_j, a_j) - np.eye(m))) < 3e-5
+
+
+def test_cfg3_full_training_step_leaves_a_canonical_mps():
+    """BaseOptimizer.train_step (baseoptimizer.py:203-244) at cfg3's size: right half-sweep, left sweep, right half-sweep =
+    390 bond updates on 60 000 images.  Afterwards the MPS must be in mixed canonical form around the special node (every
+    node to its left an isometry over (feature, left bond), every node to its right over (feature, right bond)), and the
+    updated weights evaluated by the inference path must match the fp64 oracle on a sample of the images."""
+    from bench import synthetic_pixels, full_bond_mps
+    N, D, L, B = 196, 120, 10, 60000
+    loc = N // 2
+    pix, lab = synthetic_pixels(N, B, L, seed=100)
+    nodes = full_bond_mps(N, 2, L, D, loc)
+    st = dev.SweepState(N, B, L, dev.bond_stride(nodes, loc, L, D), nat.FM_COS_SIN, nat.LOSS_SOFTMAX_XENT, torch.device("cuda", 0))
+    st.set_nodes(nodes, loc)
+    st.set_batch(pix, lab)
+    st.train_step(dev.make_opt(lr=1e-4, max_size=D, reg=1e-3, min_singular_value=0.0), loc=loc)
+    torch.cuda.synchronize()
+    assert int(st.iwork.cpu().numpy()[nat.I_N_UPDATES]) == 2 * (N - 1)
+    new_nodes = st.get_nodes()
+    assert all(np.isfinite(w).all() for w in new_nodes)
+    assert new_nodes[loc].ndim == 4
+    worst = 0.0
+    for i, w in enumerate(new_nodes):
+        a = w.astype(np.float64)
+        if i < loc:
+            g = np.einsum('miq,mir->qr', a, a)
+        elif i > loc:
+            g = np.einsum('mqk,mrk->qr', a, a)
+        else:
+            continue
+        worst = max(worst, float(np.max(np.abs(g - np.eye(g.shape[0])))))
+    assert worst < 5e-5
+    sample = np.random.default_rng(4).choice(B, 48, replace=False)
+    phi64 = o.feature_map(pix[:, sample].astype(np.float64), o.FM_COS_SIN, dtype=np.float64)
+    want = o.predict([w.astype(np.float64) for w in new_nodes], loc, phi64, L)
+    got = dev.predict(st.weights_view(), st.feat, nat.FM_COS_SIN).cpu().numpy()
+    assert rel(got[sample], want) < RTOL
