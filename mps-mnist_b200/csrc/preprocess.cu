@@ -110,6 +110,37 @@ __global__ void __launch_bounds__(256) preprocess_pool_kernel(const T* __restric
   write_sites<PRE_TI>(tile, cols / 2, (int64_t)pr * (cols / 2), t0, B, out_map, out);
 }
 
+// uint8 images, pooled: the byte format of the idx files.  4-byte loads per lane make the generic kernel instruction bound,
+// so here one thread owns one image's strip (the two raw rows under a pooled row: 2 * COLS bytes, 8-byte aligned) and reads
+// it with 8-byte loads (L1 keeps the sectors the neighbouring loads share); 256 images per CTA, sites written as 1 KB rows.
+template <typename T, bool MAXP, int COLS>
+__global__ void __launch_bounds__(256) preprocess_pool_bytes_kernel(const T* __restrict__ images, int64_t total, int rows, int64_t start,
+                                                                    int64_t B, int out_map, float* __restrict__ out) {
+  constexpr int TI = 256, NW = 2 * COLS / 8, NS = COLS / 2;
+  static_assert(COLS % 4 == 0, "row pairs must be whole 8-byte words");
+  __shared__ float tile[NS * (TI + 1)];
+  const int nstrips = rows / 2;
+  const int64_t t0 = (int64_t)(blockIdx.x / nstrips) * TI;
+  const int pr = blockIdx.x % nstrips, i = threadIdx.x;
+  if (t0 + i < B) {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(images) + wrap_row(start, t0 + i, total) * ((int64_t)rows * COLS) + (int64_t)(2 * pr) * COLS;
+    uint2 w[NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) w[k] = __ldg(reinterpret_cast<const uint2*>(p) + k);
+    auto byte_at = [&](int b) -> float {              // b is a compile-time constant after unrolling
+      const uint32_t word = (b & 4) ? w[b >> 3].y : w[b >> 3].x;
+      return px((uint8_t)((word >> (8 * (b & 3))) & 0xffu), images);
+    };
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const float a0 = byte_at(2 * s), a1 = byte_at(2 * s + 1), b0 = byte_at(COLS + 2 * s), b1 = byte_at(COLS + 2 * s + 1);
+      tile[s * (TI + 1) + i] = MAXP ? fmaxf(fmaxf(a0, a1), fmaxf(b0, b1)) : ((a0 + a1) + (b0 + b1)) * 0.25f;
+    }
+  }
+  __syncthreads();
+  write_sites<TI>(tile, NS, (int64_t)pr * NS, t0, B, out_map, out);
+}
+
 // four values starting at p; the scalar variant serves rows whose length is not a multiple of 4 (no 16-byte alignment)
 template <bool VEC, typename T>
 __device__ __forceinline__ float4 load_quad(const T* p, int valid) {
@@ -273,6 +304,15 @@ int preprocess_typed(const T* images, int64_t total, int rows, int cols, int poo
     return launch_flat<T, 1>(images, total, (int64_t)rows * cols, start, B, out_map, out, st, "trmps_preprocess_batch");
   if (rows % 2 || cols % 4 || cols > PRE_MAXCOLS)
     return bad("trmps_preprocess_batch: pooling needs an even number of rows and cols a multiple of 4, at most 64");
+  if (sizeof(T) == 1 && cols == 28) {                 // MNIST / Fashion-MNIST bytes: one thread per image strip
+    const int64_t tiles256 = ceil_div64(B, 256);
+    if (tiles256 * (rows / 2) > 0x7fffffff) return bad("trmps_preprocess_batch: batch too large");
+    const unsigned grid = (unsigned)(tiles256 * (rows / 2));
+    if (pool == TRMPS_POOL_AVG) preprocess_pool_bytes_kernel<T, false, 28><<<grid, 256, 0, st>>>(images, total, rows, start, B, out_map, out);
+    else preprocess_pool_bytes_kernel<T, true, 28><<<grid, 256, 0, st>>>(images, total, rows, start, B, out_map, out);
+    TRMPS_LAUNCH_OK("preprocess_pool_bytes_kernel");
+    return TRMPS_OK;
+  }
   const int64_t tiles = ceil_div64(B, PRE_TI);
   if (tiles * (rows / 2) > 0x7fffffff) return bad("trmps_preprocess_batch: batch too large");
   const unsigned grid = (unsigned)(tiles * (rows / 2));
