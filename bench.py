@@ -373,9 +373,9 @@ def run_ours(args, rank, local_rank, world):
                     images_per_sec=world * Bi / (pms * 1e-3), ms_per_launch=pms, bytes_per_launch=nbytes,
                     achieved=nbytes / (pms * 1e-3) / 1e9, unit="GB/s",
                     l2="%.0f MB per launch, larger than L2" % (nbytes / 1e6),
-                    # ncu --set full of the same launches (profiles/r1l_datasource_kernels_ncu.txt): dram read + write
-                    traffic={(60000, True): 0.188180e9 + 0.023254e9, (1000000, False): 3.136021e9 + 3.087183e9}.get((Bi, shrink)),
-                    traffic_source="ncu dram__bytes_read+write per launch (profiles/r1l_datasource_kernels_ncu.txt): the algorithmic "
+                    # ncu --set full of the same launches (profiles/r1m_datasource_kernels_ncu.txt): dram read + write
+                    traffic={(60000, True): 0.188178e9 + 0.022715e9, (1000000, False): 3.136020e9 + 3.086650e9}.get((Bi, shrink)),
+                    traffic_source="ncu dram__bytes_read+write per launch (profiles/r1m_datasource_kernels_ncu.txt): the algorithmic "
                                    "bytes, no re-reads; part of a 60k-image batch's output is still in L2 when the kernel ends")
 
     datasource = None
