@@ -101,9 +101,13 @@ typedef struct {
   int32_t min_size;           /* 3 in the reference                         optimizer.py:266 */
   int32_t updates_per_step;   /*                                            baseoptimizer.py:324-332 */
   int32_t use_hessian;        /* diagonal Hessian scaling                   optimizer.py:229-237 */
-  int32_t max_svd_sweeps;     /* 0 = default (30) */
+  int32_t max_svd_sweeps;     /* 0 = default (40) */
   int32_t single_site;        /* 1: single-site DMRG updates (singlesiteOptimizer.py:49-138): trmps_bond_step(site, dir)
                                  optimises the special node at `site` alone, splits it and lets node site+dir absorb S V */
+  int32_t split_impl;         /* 0: Jacobi on the Cholesky factor of the bond's Gram matrix inside one thread-block cluster
+                                 (split_factor.cu; R = 2*Ds <= 256), falling back to 1 for larger bonds;
+                                 1: Jacobi on the rows of the bond matrix itself (svd.cu) */
+  int32_t reserved;
 } trmps_opt;
 
 /* offsets (in floats) of the library-defined regions inside the caller's `work` buffer */
@@ -111,7 +115,7 @@ typedef struct {
   int64_t bondM, gradM, deltaM, hessM;   /* R x Cc each (gradM has TRMPS_S_COUNT spare floats behind it) */
   int64_t gpart;                         /* gsplit x R x Cc split-K partials of the gradient */
   int64_t f0, fd;                        /* (B, L) logits of the bond and of delta */
-  int64_t fpart;                         /* nsplit x (B, L) column-split partial logits */
+  int64_t fpart;                         /* nsplit x (B, L) column-split partial logits (sized for the FP32 SIMT forward whatever kernel runs) */
   int64_t resid;                         /* (B, L)   y - h */
   int64_t sres;                          /* (B, 2L)  resid[t,l] * phi_far[t,n] */
   int64_t hres;                          /* (B, 2L)  h(1-h)[t,l] * phi_far[t,n]^2 (Hessian only) */
@@ -121,6 +125,7 @@ typedef struct {
   int64_t red;                           /* per-CTA partial sums of the scalar reductions */
   int64_t scal;                          /* TRMPS_S_COUNT floats */
   int64_t bimg;                          /* TF32 hi/lo shared-memory images of the bond for the tensor-core forward */
+  int64_t split_ws;                      /* FP64 Gram partials, Gram matrix, Cholesky factor and the rotated factor of the split */
   int64_t total;                         /* floats the caller must allocate for `work` */
   int32_t gsplit, nsplit;                /* split-K factor of the gradient, column split of the forward */
   int32_t red_rows, svd_block;           /* rows of `red`; rows per Jacobi block */
@@ -145,6 +150,7 @@ typedef struct {
   float*   work;             /* layout.total floats */
   int32_t* iwork;            /* TRMPS_I_COUNT ints */
   void*    comm;             /* trmps_comm* or NULL when world == 1 */
+  int64_t  work_floats;      /* floats allocated behind `work`; every call checks it against the layout it computes */
 } trmps_sweep;
 
 /* inference: replaces the graph MPS.predict builds (mps.py:521-560) */

@@ -187,6 +187,10 @@ int svd_block_rows(int R, int Cc);
 // single: the bond has a unit far site (columns with n = 1 are zero): at most L * d_far singular values are non-zero
 int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, cudaStream_t st,
               float* special_out = nullptr, bool single = false);
+bool split_factor_supported(int R);
+int64_t split_ws_floats(int R);
+int split_factor(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, cudaStream_t st,
+                 float* special_out, bool single);
 int launch_special_to_bond(const float* special, float* M, float* phi_far, int Ds, int L, int64_t B, int dir, cudaStream_t st);
 int launch_site_absorb(const float* tmp, const float* node, float* special, int Ds, int L, int dir, cudaStream_t st);
 void set_flat_variant(int v);   // development switch: tile shape of the flat datasource kernel

@@ -1,0 +1,902 @@
+// Truncated bond split on a small factor that never leaves the chip  (north_star piece 4, second implementation).
+// Replaces MPSOptimizer._bond_decomposition (optimizer.py:266-321) like svd.cu does, but instead of rotating the
+// long rows of the bond matrix M (R x Cc, Cc = L * R) it works on an n x n factor, n = rows in use <= 256:
+//
+//   1. split_gram_kernel     G = M M^T in FP64 (the products of two floats are exact in double; every CTA owns a
+//                            64 x 64 tile of G and a slice of the columns, the last CTA to finish a tile adds the
+//                            slices in a fixed order -- no floating-point atomics, bit-identical on every rank)
+//   2. split_chol_kernel     G = R^T R, blocked left-looking Cholesky in FP64 on one SM; R is rounded to FP32,
+//                            scaled by a power of two so that its largest row has norm ~1, rows ranked by norm
+//   3. split_jacobi_kernel   one-sided (Hestenes) Jacobi on the ROWS of R inside ONE thread-block cluster: every CTA
+//                            holds two complete blocks of 16 rows in shared memory (a row pair is rotated by one warp:
+//                            dot products and norms are warp-local, nothing is reduced across CTAs), blocks move
+//                            between CTAs through distributed shared memory with one cluster barrier per round
+//                            (round-robin tournament over blocks).  R R^T is much closer to diagonal than
+//                            G (Drmac-Veselic preconditioning), and no rotations have to be accumulated:
+//                            J^T R = diag(sigma) W^T with R^T R = G means the rows of W^T -- the converged rows
+//                            divided by their norms -- are the eigenvectors of G, i.e. the left singular vectors of M.
+//   4. split_rank_kernel     sigma sorted, m = clamp(#{sigma > min_sv}, min_size, max_size)   (optimizer.py:294-302)
+//   5. split_project_kernel  a_j1 = U[:, :m]^T M written straight into the special-node layout, a_j = U[:, :m] into
+//                            the node slot (optimizer.py:305-317 and the transposes at :180, :125-126)
+//
+// sigma_p is the norm of row p of U^T M.  Nothing is divided by a small sigma except the normalisation of rows that
+// are numerically zero, which are set to zero like utils.check_nan does with the NaNs of tf.svd (utils.py:9-20).
+// None of the kernels is a cooperative launch, so ncu can replay each of them.
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "svd_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace trmps {
+
+// ------------------------------------------------------------------------------------------------ workspace
+constexpr int SP_KS_MAX = 16;     // column slices of the Gram product
+constexpr int SP_NMAX = 256;      // rows of the factor
+
+struct SplitWs {
+  double* gp;      // [SP_KS_MAX][R][R] Gram partials
+  double* G;       // [R][R] Gram matrix (lower triangle used)
+  double* Rd;      // [R][R] Cholesky factor, row k = row k of R (upper triangle used)
+  float* Rf;       // [R][R] R in FP32 / scale
+  float* X;        // [R + 2 JB][R] rows after the Jacobi iteration, normalised (by slot)
+  float* sig;      // [SP_NMAX] row norms after the Jacobi iteration (by slot), then sigma
+  float* scale;    // [4]: scale of Rf, largest diagonal of G
+  int32_t* cnt;    // [64] tile arrival counters (zero between launches)
+  int32_t* rowmap; // [SP_NMAX] rank -> row of R
+};
+
+int64_t split_ws_floats(int R) {
+  const int64_t RR = (int64_t)R * R;
+  return 2 * (SP_KS_MAX * RR) + 2 * RR + 2 * RR + RR + (int64_t)(R + 32) * R + SP_NMAX + 4 + 64 + SP_NMAX + 16;
+}
+
+static SplitWs split_ws(float* base, int R) {
+  const int64_t RR = (int64_t)R * R;
+  SplitWs w;
+  double* d = reinterpret_cast<double*>(base);
+  w.gp = d; d += SP_KS_MAX * RR;
+  w.G = d; d += RR;
+  w.Rd = d; d += RR;
+  float* f = reinterpret_cast<float*>(d);
+  w.Rf = f; f += RR;
+  w.X = f; f += (int64_t)(R + 32) * R;
+  w.sig = f; f += SP_NMAX;
+  w.scale = f; f += 4;
+  w.cnt = reinterpret_cast<int32_t*>(f); f += 64;
+  w.rowmap = reinterpret_cast<int32_t*>(f);
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------ 1. Gram matrix
+constexpr int GT = 64, GK = 32, GLD = GT + 2;
+
+struct GramArgs {
+  const float* M; int R, Cc, Ds; const int32_t* d_near; int ks_cols, KS; double* gp; double* G; int32_t* cnt;
+};
+
+__global__ void __launch_bounds__(256) split_gram_kernel(GramArgs a) {
+  __shared__ __align__(16) double As[GK][GLD];
+  __shared__ __align__(16) double Bs[GK][GLD];
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const int dn = *a.d_near, n = 2 * dn;
+  // lower-triangular tile (ti >= tj) from the linear tile index
+  int ti = 0, rem = blockIdx.x;
+  while (rem > ti) { rem -= ti + 1; ++ti; }
+  const int tj = rem;
+  if (ti * GT >= n) return;                    // tile outside the rows in use: the factorisation never reads it
+  const int ks = blockIdx.y;
+  const int c_begin = ks * a.ks_cols, c_end = min(a.Cc, c_begin + a.ks_cols);
+  const int tx = tid & 15, ty = tid >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  const int lrow = tid >> 2, lcg = (tid & 3) * 8;
+  const int pa = ti * GT + lrow, pb = tj * GT + lrow;
+  const float* rowa = pa < n ? a.M + (size_t)compact_to_row(pa, dn, a.Ds) * a.Cc : nullptr;
+  const float* rowb = pb < n ? a.M + (size_t)compact_to_row(pb, dn, a.Ds) * a.Cc : nullptr;
+  const bool diag = ti == tj;
+  for (int c0 = c_begin; c0 < c_end; c0 += GK) {
+    float va[8], vb[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + lcg + 4 * h;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+      if (c < c_end) {
+        if (rowa) x = __ldg(reinterpret_cast<const float4*>(rowa + c));
+        if (!diag && rowb) y = __ldg(reinterpret_cast<const float4*>(rowb + c));
+      }
+      va[4 * h] = x.x; va[4 * h + 1] = x.y; va[4 * h + 2] = x.z; va[4 * h + 3] = x.w;
+      vb[4 * h] = y.x; vb[4 * h + 1] = y.y; vb[4 * h + 2] = y.z; vb[4 * h + 3] = y.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      As[lcg + e][lrow] = (double)va[e];
+      if (!diag) Bs[lcg + e][lrow] = (double)vb[e];
+    }
+    __syncthreads();
+    const double (*Bp)[GLD] = diag ? As : Bs;
+#pragma unroll 8
+    for (int k = 0; k < GK; ++k) {
+      const double2 a01 = *reinterpret_cast<const double2*>(&As[k][ty * 4]);
+      const double2 a23 = *reinterpret_cast<const double2*>(&As[k][ty * 4 + 2]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&Bp[k][tx * 4]);
+      const double2 b23 = *reinterpret_cast<const double2*>(&Bp[k][tx * 4 + 2]);
+      const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+    }
+  }
+  // partial tile of this column slice
+  const int R = a.R;
+  double* gp = a.gp + (size_t)ks * R * R;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = ti * GT + ty * 4 + i;
+    if (p < R) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = tj * GT + tx * 4 + j;
+        if (q < R) __stcg(&gp[(size_t)p * R + q], acc[i][j]);
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int old = atomicAdd(&a.cnt[blockIdx.x], 1);
+    s_last = old == a.KS - 1;
+    if (s_last) a.cnt[blockIdx.x] = 0;          // ready for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA of this tile: add the slices in a fixed order (all slices of a row of four entries are loaded first, so
+  // the L2 round trips overlap)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = ti * GT + ty * 4 + i;
+    const int q0 = tj * GT + tx * 4;
+    if (p < R && q0 < R) {                       // R is a multiple of 4: a row of four entries is in or out as a whole
+      double2 v[SP_KS_MAX][2];
+#pragma unroll
+      for (int k = 0; k < SP_KS_MAX; ++k) {
+        if (k < a.KS) {
+          const double2* src = reinterpret_cast<const double2*>(&a.gp[((size_t)k * R + p) * R + q0]);
+          v[k][0] = __ldcg(src); v[k][1] = __ldcg(src + 1);
+        } else {
+          v[k][0] = make_double2(0.0, 0.0); v[k][1] = v[k][0];
+        }
+      }
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < SP_KS_MAX; ++k) { s0 += v[k][0].x; s1 += v[k][0].y; s2 += v[k][1].x; s3 += v[k][1].y; }
+      double2* dst = reinterpret_cast<double2*>(&a.G[(size_t)p * R + q0]);
+      dst[0] = make_double2(s0, s1); dst[1] = make_double2(s2, s3);
+      if (ti != tj) {                              // G is symmetric: store the mirror image too (the factorisation reads columns as rows)
+        a.G[(size_t)q0 * R + p] = s0; a.G[(size_t)(q0 + 1) * R + p] = s1;
+        a.G[(size_t)(q0 + 2) * R + p] = s2; a.G[(size_t)(q0 + 3) * R + p] = s3;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 2. Cholesky
+// Left-looking, panels of CW columns, one SM.  Rd[k][i] (i >= k) is stored row-wise, so thread i reads the entries of
+// column i of all earlier rows with unit stride.  Per panel:
+//   update   P[i][c] = G[i][c0+c] - sum_{k<c0} Rd[k][i] Rd[k][c0+c]     all 1024 threads (k split four ways), panel in registers
+//   diagonal the 16 x 16 diagonal block is factorised by ONE warp in registers (lane = row, values exchanged by shuffles):
+//            the only sequential part, 16 dependent steps without a block barrier
+//   solve    every row below does its own forward substitution with the factor of the diagonal block (no barrier)
+// (A version that kept the panel in shared memory and took a block barrier per column spent 1260 cycles per column on
+// shared-memory traffic: 600 wavefronts per column.)
+// A pivot that is not safely positive (rank-deficient bond: the reference's initial MPS has many exactly dependent rows) is
+// replaced by a tiny one and its column is dropped: that row of R then carries a singular value ~1e-7 sigma_max, i.e.
+// zero in FP32 terms.
+constexpr int CW = 16, CT = 256, CNE = CW * SP_NMAX / CT;   // CNE: panel entries per thread
+
+struct CholArgs {
+  const double* G; double* Rd; float* Rf; int R; const int32_t* d_near; float* scale; int32_t* rowmap; float* dbg;
+};
+
+// 1/sqrt(x) for x in (1e-14, 2]: MUFU seed in single precision + one Newton step in double (relative error < 1e-13)
+__device__ __forceinline__ double rsqrt_seeded(double x) {
+  const double y = (double)rsqrt_fast((float)x);
+  return y * fma(-0.5 * x * y, y, 1.5);
+}
+
+__global__ void __launch_bounds__(CT) split_chol_kernel(CholArgs a) {
+  extern __shared__ __align__(16) double csm[];
+  double (*D)[CW] = reinterpret_cast<double (*)[CW]>(csm);                                             // D[k][c] = Rd[k][c0 + c], k < c0
+  double (*part)[CT] = reinterpret_cast<double (*)[CT]>(csm + CW * SP_NMAX);                           // part[c][thread]: partial sums of the k groups 1..
+  double (*Gs)[SP_NMAX] = reinterpret_cast<double (*)[SP_NMAX]>(csm + CW * SP_NMAX + CW * CT);             // Gs[c][i] = G[i][c0 + c]
+  __shared__ float nrm_part[CW][SP_NMAX / 32];
+  __shared__ __align__(16) double Dg[CW][CW + 1];        // diagonal block before / its factor after
+  __shared__ double rinv_s[CW];
+  __shared__ double red[CT / 32];
+  __shared__ float nrm[SP_NMAX];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = 2 * *a.d_near, R = a.R;
+  // largest diagonal entry -> pivot threshold and the power-of-two scale of the FP32 copy
+  double dmax = 0.0;
+  for (int i = tid; i < n; i += CT) dmax = fmax(dmax, a.G[(size_t)i * R + i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  if (lane == 0) red[warp] = dmax;
+  __syncthreads();
+  dmax = 0.0;
+  for (int w = 0; w < CT / 32; ++w) dmax = fmax(dmax, red[w]);
+  const double tolp = (double)n * 2.3e-16 * dmax;
+  const double sq_tolp = sqrt(tolp > 0.0 ? tolp : 1e-300), inv_dmax = dmax > 0.0 ? 1.0 / dmax : 0.0, rs_dmax = dmax > 0.0 ? rsqrt(dmax) : 0.0;
+  int ex = 0;
+  if (dmax > 0.0) frexp(sqrt(dmax), &ex);
+  const double inv_scale = ldexp(1.0, -ex);                // Rf = Rd * 2^-ex: largest row norm in [0.5, ~16)
+  const bool timer = a.dbg != nullptr && warp == 0;      // (BAR.SYNC defers its block to the next dependent instruction, so a
+  long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = timer ? clock64() : 0;   //  phase's wait shows up in the NEXT phase's counter)
+  auto tick = [&](int k) { if (timer) { const long long now = clock64(); tacc[k] += now - tprev; tprev = now; } };
+  for (int c0 = 0; c0 < n; c0 += CW) {
+    const int w = min(CW, n - c0);
+    // rows c0 .. n-1 of the panel, padded to whole warps; the k range of the update is split over as many thread groups as fit
+    const int nr = n - c0, nrp = (nr + 31) & ~31, ngr = CT / nrp;
+    const int g = tid / nrp, il = tid - g * nrp, irow = c0 + il;
+    const bool upd = g < ngr && il < nr;                   // takes part in the update
+    const bool mine = g == 0 && il < nr;                   // owns row irow of the panel
+    auto rd_load = [&](int b, double (&r)[8]) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = g + ngr * (8 * b + u);
+        r[u] = (upd && k < c0) ? __ldcg(&a.Rd[(size_t)k * R + irow]) : 0.0;
+      }
+    };
+    // ---- columns c0 .. c0+w-1 of G (stored in full: read as rows, unit stride), D[k][c] = Rd[k][c0 + c] and the first batch
+    //      of this thread's entries of R: all issued before the first one is used (an L2 round trip is ~800 cycles here)
+    double r0[8], r1[8];
+    {
+      double gv[CNE], dv[CNE];
+#pragma unroll
+      for (int u = 0; u < CNE; ++u) {
+        const int e = tid + u * CT, c = e / SP_NMAX, j = e % SP_NMAX;        // CW * SP_NMAX = CNE * CT entries
+        gv[u] = (c < w && j >= c0 && j < n) ? __ldcg(&a.G[(size_t)(c0 + c) * R + j]) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < CNE; ++u) {
+        const int e = tid + u * CT, k = e / CW, c = e % CW;
+        dv[u] = (e < c0 * CW && c < w) ? __ldcg(&a.Rd[(size_t)k * R + c0 + c]) : 0.0;
+      }
+      rd_load(0, r0);
+#pragma unroll
+      for (int u = 0; u < CNE; ++u) {
+        const int e = tid + u * CT;
+        Gs[e / SP_NMAX][e % SP_NMAX] = gv[u];
+        if (e < c0 * CW) D[e / CW][e % CW] = dv[u];
+      }
+    }
+    __syncthreads();
+    tick(0);
+    // ---- update: acc[c] = sum over this group's k of Rd[k][irow] Rd[k][c0+c]; the next batch of loads is in flight while
+    //      the current one is used
+    double acc[CW];
+#pragma unroll
+    for (int c = 0; c < CW; ++c) acc[c] = 0.0;
+    const int nbatch = (c0 + 8 * ngr - 1) / (8 * ngr);
+    auto rd_use = [&](int b, const double (&r)[8]) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = min(g + ngr * (8 * b + u), c0 - 1);   // r[u] is zero beyond the range
+#pragma unroll
+        for (int c = 0; c < CW; ++c) acc[c] = fma(r[u], D[k][c], acc[c]);
+      }
+    };
+    for (int b = 0; b < nbatch; b += 2) {
+      rd_load(b + 1, r1);
+      rd_use(b, r0);
+      rd_load(b + 2, r0);
+      rd_use(b + 1, r1);
+    }
+    if (g > 0 && upd) {
+#pragma unroll
+      for (int c = 0; c < CW; ++c) part[c][tid] = acc[c];
+    }
+    __syncthreads();
+    tick(1);
+    double p[CW];
+    if (mine) {
+#pragma unroll
+      for (int c = 0; c < CW; ++c) {
+        double sacc = acc[c];
+        for (int gg = 1; gg < ngr; ++gg) sacc += part[c][gg * nrp + il];
+        p[c] = Gs[c][irow] - sacc;
+      }
+      if (il < CW) {
+#pragma unroll
+        for (int c = 0; c < CW; ++c) Dg[il][c] = p[c];
+      }
+    }
+    __syncthreads();
+    tick(2);
+    // ---- diagonal block: one warp, lane r holds row r, 16 dependent steps
+    if (warp == 0) {
+      const int r = lane & 15;
+      double d[CW];
+#pragma unroll
+      for (int c = 0; c < CW; ++c) d[c] = (r < nr) ? Dg[r][c] : 0.0;
+#pragma unroll
+      for (int c = 0; c < CW; ++c) {
+        const double piv = __shfl_sync(0xffffffffu, d[c], c);
+        const bool drop = !(piv > tolp) || c >= w;
+        const double rinv = drop ? 0.0 : rsqrt_seeded(piv * inv_dmax) * rs_dmax;
+        const double lkk = drop ? sq_tolp : piv * rinv;
+        const double l = r == c ? lkk : d[c] * rinv;       // l[r][c], meaningful for r >= c
+        d[c] = l;
+#pragma unroll
+        for (int cc = c + 1; cc < CW; ++cc) {
+          const double t = __shfl_sync(0xffffffffu, l, cc);   // l[cc][c]
+          d[cc] = fma(-l, t, d[cc]);
+        }
+        if (lane == 0) rinv_s[c] = rinv;
+      }
+      if (lane < CW) {
+#pragma unroll
+        for (int c = 0; c < CW; ++c) Dg[r][c] = c <= r ? d[c] : 0.0;
+      }
+    }
+    __syncthreads();
+    tick(3);
+    // ---- rows below the diagonal block: forward substitution; rows of the block: their row of its factor.  The finished
+    //      rows go back into Gs (which already holds zeros left of the panel and beyond n)
+    if (mine) {
+      if (il >= CW) {
+#pragma unroll
+        for (int c = 0; c < CW; ++c) {
+          const double l = p[c] * rinv_s[c];
+          p[c] = l;
+#pragma unroll
+          for (int cc = c + 1; cc < CW; ++cc) p[cc] = fma(-l, Dg[cc][c], p[cc]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CW; ++c) p[c] = Dg[il][c];
+      }
+#pragma unroll
+      for (int c = 0; c < CW; ++c) Gs[c][irow] = p[c];
+    }
+    __syncthreads();
+    // ---- rows c0 .. c0+w-1 of R out (unit stride); squared norms of the FP32 rows: warp sums, then the eight warps of a
+    //      row in a fixed order
+#pragma unroll
+    for (int u = 0; u < CNE; ++u) {
+      const int e = tid + u * CT, c = e / SP_NMAX, j = e % SP_NMAX;
+      float f = 0.f;
+      if (c < w && j < R) {
+        const double v = Gs[c][j];
+        __stcg(&a.Rd[(size_t)(c0 + c) * R + j], v);
+        f = (float)(v * inv_scale);
+        a.Rf[(size_t)(c0 + c) * R + j] = f;
+      }
+      float sq = f * f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      if (lane == 0) nrm_part[c][(e % SP_NMAX) / 32] = sq;
+    }
+    __syncthreads();
+    if (tid < w) {
+      float sq = 0.f;
+#pragma unroll
+      for (int q = 0; q < SP_NMAX / 32; ++q) sq += nrm_part[tid][q];
+      nrm[c0 + tid] = sq;
+    }
+    tick(4);
+  }
+  // ---- ranking of the rows by norm
+  __syncthreads();
+  if (tid < n) {
+    const float sp = nrm[tid];
+    int rank = 0;
+    for (int o = 0; o < n; ++o) {
+      const float so = nrm[o];
+      rank += (so > sp) || (so == sp && o < tid);
+    }
+    a.rowmap[rank] = tid;
+  }
+  tick(5);
+  if (timer && lane == 0) for (int k = 0; k < 6; ++k) a.dbg[k] = (float)tacc[k];
+  if (tid == 0) { a.scale[0] = (float)ldexp(1.0, ex); a.scale[1] = (float)dmax; }
+}
+
+// ------------------------------------------------------------------------------------------------ 3. Jacobi
+constexpr int JB = 16;                 // rows per block
+constexpr int JWARPS = 8, JT = 32 * JWARPS;
+constexpr int JLD = SP_NMAX + 4;       // row stride in shared memory (floats): 16-byte rows, conflict-free float4 access;
+                                       // float SP_NMAX of a row carries its squared norm through the rotations
+constexpr int JCL_MAX = 8;             // CTAs per cluster = block pairs per round
+constexpr int JPH_CROSS = 8, JPH_ALL = 16;
+
+struct JacArgs {
+  const float* Rf; int R; const int32_t* rowmap; const int32_t* d_near; float* X; float* sig; int32_t* iscal;
+  float tol, stop; int max_sweeps; int csize; float* dbg;   // dbg: 4 floats, cycles of CTA 0 in (rotations, cluster barrier, -, -)
+};
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float s) {
+  s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); return fmaf(a.w, b.w, s);
+}
+__device__ __forceinline__ void rot4(float4& x, float4& y, float sn, float tau) {
+  // Rutishauser's form x' = x - s (y + tau x), y' = y + s (x - tau y): norm-preserving in FP32 even when cos rounds to 1
+  float u, w;
+  u = x.x; w = y.x; x.x = fmaf(-sn, fmaf(tau, u, w), u); y.x = fmaf(sn, fmaf(-tau, w, u), w);
+  u = x.y; w = y.y; x.y = fmaf(-sn, fmaf(tau, u, w), u); y.y = fmaf(sn, fmaf(-tau, w, u), w);
+  u = x.z; w = y.z; x.z = fmaf(-sn, fmaf(tau, u, w), u); y.z = fmaf(sn, fmaf(-tau, w, u), w);
+  u = x.w; w = y.w; x.w = fmaf(-sn, fmaf(tau, u, w), u); y.w = fmaf(sn, fmaf(-tau, w, u), w);
+}
+
+// a row of the factor spread over one warp: lane holds columns 4 lane .. 4 lane + 3 (and 128 + the same when WIDE);
+// nrm = squared norm, carried through the rotations (al' = al - t ga, be' = be + t ga, exact for the exact Jacobi angle)
+// and refreshed from the data once per sweep: it only steers the angle, so its rounding drift cannot bias the
+// singular values.
+template <bool WIDE>
+struct JRow {
+  float4 lo, hi; float nrm;
+  __device__ __forceinline__ void load(const float* p, int lane) {
+    lo = *reinterpret_cast<const float4*>(p + lane * 4);
+    if (WIDE) hi = *reinterpret_cast<const float4*>(p + 128 + lane * 4);
+    nrm = p[SP_NMAX];
+  }
+  __device__ __forceinline__ void store(float* p, int lane) const {
+    *reinterpret_cast<float4*>(p + lane * 4) = lo;
+    if (WIDE) *reinterpret_cast<float4*>(p + 128 + lane * 4) = hi;
+    if (lane == 0) p[SP_NMAX] = nrm;
+  }
+};
+
+__device__ __forceinline__ float rcp_fast(float x) {        // one MUFU.RCP (callers keep x in [1, 2])
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Jacobi rotation of a row pair from its three inner products: sn, tau for Rutishauser's form, cs = cos, tg = tan * ga
+// (the amount the squared norms change by), relg = |cos of the angle between the rows| before the rotation (0 when the
+// pair is left alone: already orthogonal to rounding, or one row numerically zero).  Half-angle form, see rotation_params.
+struct JRot { float sn, tau, cs, tg, relg; };
+__device__ __forceinline__ JRot jacobi_angle(float al, float be, float ga, float tol) {
+  const float big = fmaxf(al, be), small = fminf(al, be);
+  const float rr = rsqrt_fast(al) * rsqrt_fast(be);
+  const float d = (be - al) * rr;
+  const bool can = small > 1e-30f && small > 1e-24f * big;
+  const float g = ga * rr;                                      // cosine of the angle between the rows
+  const float relg = fabsf(g);
+  const bool rot = can && relg > tol;
+  const float rh = rsqrt_fast(fmaf(d, d, 4.f * g * g));
+  const float c2 = fabsf(d) * rh;
+  const float xx = fmaf(0.5f, c2, 0.5f);
+  const float rc = rsqrt_fast(xx);
+  const float cc = xx * rc;
+  const float s1 = ((d >= 0.f) ? g : -g) * rh * rc;
+  JRot r;
+  r.sn = rot ? s1 : 0.f;
+  r.cs = rot ? cc : 1.f;
+  r.tau = rot ? s1 * rcp_fast(1.f + cc) : 0.f;
+  r.tg = rot ? s1 * rc * ga : 0.f;
+  r.relg = rot ? relg : 0.f;
+  return r;
+}
+
+template <bool WIDE>
+__device__ __forceinline__ void jacobi_apply(JRow<WIDE>& x, JRow<WIDE>& y, const JRot& r) {
+  rot4(x.lo, y.lo, r.sn, r.tau);
+  if (WIDE) rot4(x.hi, y.hi, r.sn, r.tau);
+  x.nrm = fmaxf(x.nrm - r.tg, 0.f);
+  y.nrm = fmaxf(y.nrm + r.tg, 0.f);
+}
+
+template <bool WIDE>
+__device__ __forceinline__ float jdot(const JRow<WIDE>& x, const JRow<WIDE>& y) {
+  float s = dot4(x.lo, y.lo, 0.f);
+  if (WIDE) s += dot4(x.hi, y.hi, 0.f);
+  return s;
+}
+
+// Two steps on four rows held in registers: (xa,ya), (xb,yb), then (xa,yb), (xb,ya).  All six inner products of the four
+// rows are reduced across the warp at once (six interleaved shuffle chains instead of two dependent rounds of two); the
+// inner products the second step needs follow from the first step's rotations by linearity, so the second pair of
+// angles does not wait for the rotated rows.  `single`: first step only.  Returns the largest |cos| rotated away.
+template <bool WIDE>
+__device__ __forceinline__ float jacobi_quad(JRow<WIDE>& xa, JRow<WIDE>& xb, JRow<WIDE>& ya, JRow<WIDE>& yb, float tol, bool single) {
+  float p_aa = jdot(xa, ya), p_bb = jdot(xb, yb), p_ab = jdot(xa, yb), p_ba = jdot(xb, ya), p_xx = jdot(xa, xb), p_yy = jdot(ya, yb);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    p_aa += __shfl_xor_sync(0xffffffffu, p_aa, o);
+    p_bb += __shfl_xor_sync(0xffffffffu, p_bb, o);
+    p_ab += __shfl_xor_sync(0xffffffffu, p_ab, o);
+    p_ba += __shfl_xor_sync(0xffffffffu, p_ba, o);
+    p_xx += __shfl_xor_sync(0xffffffffu, p_xx, o);
+    p_yy += __shfl_xor_sync(0xffffffffu, p_yy, o);
+  }
+  const JRot r1 = jacobi_angle(xa.nrm, ya.nrm, p_aa, tol);      // xa' = c1 xa - s1 ya, ya' = s1 xa + c1 ya
+  const JRot r2 = jacobi_angle(xb.nrm, yb.nrm, p_bb, tol);      // xb' = c2 xb - s2 yb, yb' = s2 xb + c2 yb
+  jacobi_apply<WIDE>(xa, ya, r1);
+  jacobi_apply<WIDE>(xb, yb, r2);
+  float worst = fmaxf(r1.relg, r2.relg);
+  if (!single) {
+    // <xa', yb'> and <xb', ya'> from the products before the first step
+    const float q_ab = r1.cs * r2.sn * p_xx + r1.cs * r2.cs * p_ab - r1.sn * r2.sn * p_ba - r1.sn * r2.cs * p_yy;
+    const float q_ba = r2.cs * r1.sn * p_xx + r2.cs * r1.cs * p_ba - r2.sn * r1.sn * p_ab - r2.sn * r1.cs * p_yy;
+    const JRot r3 = jacobi_angle(xa.nrm, yb.nrm, q_ab, tol);
+    const JRot r4 = jacobi_angle(xb.nrm, ya.nrm, q_ba, tol);
+    jacobi_apply<WIDE>(xa, yb, r3);
+    jacobi_apply<WIDE>(xb, ya, r4);
+    worst = fmaxf(worst, fmaxf(r3.relg, r4.relg));
+  }
+  return worst;
+}
+
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+
+// Inside a CTA the 32 rows of its two blocks are rotated by 8 warps with 2 x 2 register blocking: a warp holds two rows
+// x_a, x_b in registers over several phases, fetches two rows y_a, y_b per phase from shared memory and rotates
+// (x_a,y_a), (x_b,y_b), then (x_a,y_b), (x_b,y_a): four rotations per two rows moved through shared memory (a row per
+// rotation made shared-memory bandwidth the limit: 64 KB per step).  Cross-block pairs: 8 phases.  Pairs inside a block
+// (once per sweep): the same scheme applied to halves, quarters, eighths of a block (4 + 2 + 1 phases) and a last phase
+// for the pairs inside the groups of two: 31 steps in all, the minimum for 32 rows.
+template <bool WIDE>
+__global__ void __launch_bounds__(JT) split_jacobi_kernel(JacArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) float jsm[];                 // [2 buffers][2 slots][JB][JLD]
+  __shared__ float wmax[2][JCL_MAX];
+  __shared__ float wwarp[JWARPS];
+  __shared__ uchar4 tab_rows[JPH_ALL][JWARPS];
+  __shared__ unsigned char tab_flags[JPH_ALL][JWARPS];         // 1: load x rows, 2: store x rows, 4: first half only
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int crank = (int)cluster.block_rank();
+  const int n = 2 * *a.d_near, R = a.R;
+  const int nb = (n + JB - 1) / JB;
+  int nbe = nb + (nb & 1);
+  if (nbe < 2) nbe = 2;
+  if (nbe > 2 * a.csize) nbe = 2 * a.csize;                    // (the host sizes the cluster for R, so this never binds)
+  const int h = nbe / 2, rounds = nbe - 1;
+  const bool active = crank < h;
+  auto buf = [&](int b, int slot, int r) -> float* { return jsm + ((size_t)((b * 2 + slot) * JB + r)) * JLD; };
+  if (tid < JPH_ALL * JWARPS) {
+    const int ph = tid / JWARPS, w = tid % JWARPS;
+    int xa, xb, ya, yb, fl;
+    if (ph < 8) { const int t = ph, y = 16 + 2 * ((w + t) % 8); xa = 2 * w; xb = xa + 1; ya = y; yb = y + 1; fl = (t == 0 ? 1 : 0) | (t == 7 ? 2 : 0); }
+    else if (ph < 12) { const int t = ph - 8, g = 16 * (w / 4), q = w % 4, y = g + 8 + 2 * ((q + t) % 4); xa = g + 2 * q; xb = xa + 1; ya = y; yb = y + 1; fl = (t == 0 ? 1 : 0) | (t == 3 ? 2 : 0); }
+    else if (ph < 14) { const int t = ph - 12, g = 8 * (w / 2), q = w % 2, y = g + 4 + 2 * ((q + t) % 2); xa = g + 2 * q; xb = xa + 1; ya = y; yb = y + 1; fl = (t == 0 ? 1 : 0) | (t == 1 ? 2 : 0); }
+    else if (ph == 14) { const int g = 4 * w; xa = g; xb = g + 1; ya = g + 2; yb = g + 3; fl = 3; }
+    else { const int g = 4 * w; xa = g; ya = g + 1; xb = g + 2; yb = g + 3; fl = 7; }
+    tab_rows[ph][w] = make_uchar4((unsigned char)xa, (unsigned char)xb, (unsigned char)ya, (unsigned char)yb);
+    tab_flags[ph][w] = (unsigned char)fl;
+  }
+  // ---- load: position p holds block p; CTA j has positions j (slot 0) and nbe-1-j (slot 1)
+  for (int e = tid; e < 2 * JB * (JLD / 4); e += JT) {
+    const int c4 = e % (JLD / 4), r = (e / (JLD / 4)) % JB, slot = e / (JB * (JLD / 4));
+    const int blk = slot == 0 ? crank : nbe - 1 - crank;
+    const int rank = blk * JB + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active && rank < n && c4 * 4 < n) v = __ldg(reinterpret_cast<const float4*>(a.Rf + (size_t)a.rowmap[rank] * R) + c4);   // columns >= n of Rf are zero
+    *reinterpret_cast<float4*>(buf(0, slot, r) + c4 * 4) = v;
+    *reinterpret_cast<float4*>(buf(1, slot, r) + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (tid < 2 * JCL_MAX) (&wmax[0][0])[tid] = 0.f;
+  __syncthreads();
+  cluster_arrive_release();
+  cluster_wait_acquire();
+  // where this CTA's two blocks go after a round: position 0 stays, the others move one place round the ring 1 .. nbe-1
+  int dcta0, dslot0, dcta1, dslot1;
+  if (crank == 0) { dcta0 = 0; dslot0 = 0; } else if (crank + 1 < h) { dcta0 = crank + 1; dslot0 = 0; } else { dcta0 = h - 1; dslot0 = 1; }
+  if (crank == 0) { dcta1 = h > 1 ? 1 : 0; dslot1 = h > 1 ? 0 : 1; } else { dcta1 = crank - 1; dslot1 = 1; }
+  int cur = 0, sweeps_used = 0;
+  const bool timer = a.dbg != nullptr && crank == 0 && warp == 0;     // warp-uniform: a per-thread branch would make the shuffles divergence-checked
+  long long tacc[2] = {0, 0}, tprev = timer ? clock64() : 0;
+  auto tick = [&](int k) { if (timer) { const long long now = clock64(); tacc[k] += now - tprev; tprev = now; } };
+  for (int sweep = 0; sweep < a.max_sweeps; ++sweep) {
+    float worst = 0.f;
+    for (int r = 0; r < rounds; ++r) {
+      if (active) {
+        float* base = jsm + (size_t)cur * 2 * JB * JLD;
+        // the last phase of a round stores every row: it stores them where they are needed next (another CTA's shared memory)
+        float *dst0, *dst1;
+        if (rounds > 1) { dst0 = cluster.map_shared_rank(buf(cur ^ 1, dslot0, 0), dcta0); dst1 = cluster.map_shared_rank(buf(cur ^ 1, dslot1, 0), dcta1); }
+        else { dst0 = base; dst1 = base + (size_t)JB * JLD; }
+        auto dstrow = [&](int row) -> float* { return (row < JB ? dst0 : dst1) + (size_t)(row % JB) * JLD; };
+        if (r == 0) {
+          // squared norms from the data (four rows per warp)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float* p = base + (size_t)(4 * warp + k) * JLD;
+            const float4 x0 = *reinterpret_cast<const float4*>(p + lane * 4);
+            float al = dot4(x0, x0, 0.f);
+            if (WIDE) { const float4 x1 = *reinterpret_cast<const float4*>(p + 128 + lane * 4); al += dot4(x1, x1, 0.f); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) al += __shfl_xor_sync(0xffffffffu, al, o);
+            if (lane == 0) p[SP_NMAX] = al;
+          }
+          __syncthreads();
+        }
+        const int nph = r == 0 ? JPH_ALL : JPH_CROSS;
+        JRow<WIDE> xa, xb, ya, yb;
+        for (int ph = 0; ph < nph; ++ph) {
+          const uchar4 rw = tab_rows[ph][warp];
+          const int fl = tab_flags[ph][warp];
+          if (fl & 1) { xa.load(base + (size_t)rw.x * JLD, lane); xb.load(base + (size_t)rw.y * JLD, lane); }
+          ya.load(base + (size_t)rw.z * JLD, lane); yb.load(base + (size_t)rw.w * JLD, lane);
+          worst = fmaxf(worst, jacobi_quad<WIDE>(xa, xb, ya, yb, a.tol, (fl & 4) != 0));
+          if (ph == nph - 1) {
+            ya.store(dstrow(rw.z), lane); yb.store(dstrow(rw.w), lane);
+            xa.store(dstrow(rw.x), lane); xb.store(dstrow(rw.y), lane);
+          } else {
+            ya.store(base + (size_t)rw.z * JLD, lane); yb.store(base + (size_t)rw.w * JLD, lane);
+            if (fl & 2) { xa.store(base + (size_t)rw.x * JLD, lane); xb.store(base + (size_t)rw.y * JLD, lane); }
+            __syncthreads();
+          }
+        }
+      }
+      if (r == rounds - 1) {
+        // sweep maximum of |cos| over the rotated pairs -> every CTA
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+        if (lane == 0) wwarp[warp] = worst;
+        __syncthreads();
+        if (tid < a.csize) {
+          float m = 0.f;
+          for (int w = 0; w < JWARPS; ++w) m = fmaxf(m, wwarp[w]);
+          float* dstw = cluster.map_shared_rank(&wmax[sweep & 1][crank], tid);
+          *dstw = active ? m : 0.f;
+        }
+      }
+      tick(0);
+      cluster_arrive_release();
+      cluster_wait_acquire();
+      tick(1);
+      if (rounds > 1) cur ^= 1;
+    }
+    sweeps_used = sweep + 1;
+    float wall = 0.f;
+    for (int k = 0; k < a.csize; ++k) wall = fmaxf(wall, wmax[sweep & 1][k]);
+    if (wall < a.stop) break;             // quadratic convergence: what this sweep left behind is O(stop^2)
+  }
+  // ---- normalised rows (= eigenvectors of G) and their norms, by slot index
+  if (active) {
+    for (int rr = warp; rr < 2 * JB; rr += JWARPS) {
+      const float* px = buf(cur, rr / JB, rr % JB) + lane * 4;
+      float4 x0 = *reinterpret_cast<const float4*>(px), x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (WIDE) x1 = *reinterpret_cast<const float4*>(px + 128);
+      float al = dot4(x0, x0, 0.f);
+      if (WIDE) al = dot4(x1, x1, al);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) al += __shfl_xor_sync(0xffffffffu, al, o);
+      const float nr = sqrtf(al);
+      const float inv = nr > 1e-30f ? 1.f / nr : 0.f;           // utils.check_nan: a direction that does not exist is zero
+      const int slot_row = crank * 2 * JB + rr;
+      float* out = a.X + (size_t)slot_row * R;
+      x0.x *= inv; x0.y *= inv; x0.z *= inv; x0.w *= inv;
+      x1.x *= inv; x1.y *= inv; x1.z *= inv; x1.w *= inv;
+      if (lane * 4 < R) *reinterpret_cast<float4*>(out + lane * 4) = x0;
+      if (128 + lane * 4 < R) *reinterpret_cast<float4*>(out + 128 + lane * 4) = x1;
+      if (lane == 0) a.sig[slot_row] = nr;
+    }
+  }
+  if (timer && lane == 0) for (int k = 0; k < 2; ++k) a.dbg[k] = (float)tacc[k];
+  if (crank == 0 && tid == 0) {
+    a.iscal[TRMPS_I_SVD_SWEEPS] = sweeps_used;
+    a.iscal[TRMPS_I_N_SWEEPS] += sweeps_used;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 4. ranking, m
+struct RankArgs {
+  float* sig; const float* scale; int nslots; int R; const int32_t* d_near; const int32_t* d_far; int ncol_blocks;
+  float* sv; int32_t* order; int32_t* iscal; int32_t* dim_out; float min_sv; int max_size, min_size;
+};
+
+__global__ void __launch_bounds__(SP_NMAX) split_rank_kernel(RankArgs a) {
+  __shared__ float sg[SP_NMAX];
+  __shared__ int s_count;
+  const int tid = threadIdx.x;
+  const int n = 2 * *a.d_near;
+  const int nb = (n + JB - 1) / JB;
+  int nbe = nb + (nb & 1);
+  if (nbe < 2) nbe = 2;
+  const int nslots = min(a.nslots, nbe * JB);
+  if (tid == 0) s_count = 0;
+  sg[tid] = tid < nslots ? a.sig[tid] * a.scale[0] : -1.f;
+  __syncthreads();
+  const int kmax = min(n, a.ncol_blocks * (*a.d_far));
+  if (tid < nslots) {
+    const float sp = sg[tid];
+    int rank = 0;
+    for (int o = 0; o < nslots; ++o) {
+      const float so = sg[o];
+      rank += (so > sp) || (so == sp && o < tid);
+    }
+    if (rank < a.R) { a.sv[rank] = rank < n ? sp : 0.f; a.order[rank] = rank < n ? tid : -1; }
+    if (rank < kmax && sp > a.min_sv) atomicAdd(&s_count, 1);
+  }
+  for (int p = nslots + tid; p < a.R; p += SP_NMAX) { a.sv[p] = 0.f; a.order[p] = -1; }
+  __syncthreads();
+  if (tid == 0) {
+    int m = s_count;
+    if (m < a.min_size) m = a.min_size;
+    else if (m > a.max_size) m = a.max_size;
+    if (m > n) m = n;
+    a.iscal[TRMPS_I_M] = m;
+    *a.dim_out = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 5. projection
+// a_j1[q][col] = sum_p U^T[q][p] M[row(p)][col], q < m, written into the special-node layout; a_j into the node slot.
+constexpr int PT = 64, PK = 16, PLD = PT + 4;
+
+struct ProjArgs {
+  const float* M; const float* X; const int32_t* order; const int32_t* iscal; const int32_t* d_near;
+  int R, Cc, Ds, L, dir; float* node; float* special; int ncol_tiles;
+};
+
+__global__ void __launch_bounds__(256) split_project_kernel(ProjArgs a) {
+  __shared__ __align__(16) float Us[PK][PLD];
+  __shared__ __align__(16) float Ms[PK][PLD];
+  const int tid = threadIdx.x;
+  const int Ds = a.Ds, dn = *a.d_near, n = 2 * dn, m = a.iscal[TRMPS_I_M];
+  if ((int)blockIdx.x >= a.ncol_tiles) {
+    // a_j: node[mm][x][y]: right -> (i = x, q = y); left -> (q = x, i = y)                  optimizer.py:305-307, :125
+    const int64_t n_node = (int64_t)2 * Ds * Ds;
+    const int nblk = gridDim.x - a.ncol_tiles;
+    for (int64_t idx = (int64_t)((blockIdx.x - a.ncol_tiles) + blockIdx.y * nblk) * 256 + tid; idx < n_node;
+         idx += (int64_t)nblk * gridDim.y * 256) {
+      const int y = (int)(idx % Ds), x = (int)((idx / Ds) % Ds), mm = (int)(idx / ((int64_t)Ds * Ds));
+      const int i = a.dir > 0 ? x : y, qq = a.dir > 0 ? y : x;
+      float v = 0.f;
+      if (qq < m && i < dn) v = a.X[(size_t)a.order[qq] * a.R + mm * dn + i];
+      a.node[idx] = v;
+    }
+    return;
+  }
+  const int q0 = blockIdx.y * PT, col0 = blockIdx.x * PT;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // loaders: U tile: thread -> (q = tid / 4, 4 consecutive p); M tile: thread -> (k = tid / 16, 4 consecutive cols)
+  const int uq = tid >> 2, up = (tid & 3) * 4;
+  const int qglob = q0 + uq;
+  const float* urow = (qglob < m) ? a.X + (size_t)a.order[qglob] * a.R : nullptr;
+  const int mk = tid >> 4, mc = (tid & 15) * 4;
+  for (int p0 = 0; p0 < n; p0 += PK) {
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
+    if (urow && p0 + up < n) u = *reinterpret_cast<const float4*>(urow + p0 + up);    // n even, tail entries of X rows are zero
+    const int p = p0 + mk;
+    if (p < n && col0 + mc < a.Cc) v = __ldg(reinterpret_cast<const float4*>(a.M + (size_t)compact_to_row(p, dn, Ds) * a.Cc + col0 + mc));
+    __syncthreads();
+    Us[up][uq] = u.x; Us[up + 1][uq] = u.y; Us[up + 2][uq] = u.z; Us[up + 3][uq] = u.w;
+    *reinterpret_cast<float4*>(&Ms[mk][mc]) = v;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&Us[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Ms[k][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+  }
+  // special[ln][x][y]: right -> (q = x, k = y); left -> (k = x, q = y)                         optimizer.py:309-317, :180, :126
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = q0 + ty * 4 + i;
+    if (q >= Ds) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = col0 + tx * 4 + j;
+      if (col >= a.Cc) continue;
+      const int ln = col / Ds, k = col % Ds;
+      const float v = q < m ? acc[i][j] : 0.f;
+      const size_t o = a.dir > 0 ? ((size_t)ln * Ds + q) * Ds + k : ((size_t)ln * Ds + k) * Ds + q;
+      a.special[o] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+bool split_factor_supported(int R) { return R <= SP_NMAX && R % 16 == 0; }
+
+int split_factor(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, cudaStream_t st,
+                 float* special_out, bool single) {
+  const int Ds = s->Ds, L = s->L, R = 2 * Ds, Cc = 2 * L * Ds;
+  SplitWs w = split_ws(s->work + lay.split_ws, R);
+  float* M = s->work + lay.bondM;
+  // 1. Gram
+  GramArgs ga;
+  ga.M = M; ga.R = R; ga.Cc = Cc; ga.Ds = Ds; ga.d_near = g.d_near; ga.gp = w.gp; ga.G = w.G; ga.cnt = w.cnt;
+  const int T = (R + GT - 1) / GT, ntiles = T * (T + 1) / 2;
+  const int chunks = (Cc + GK - 1) / GK;
+  int ks = 160 / ntiles;
+  if (ks < 1) ks = 1;
+  if (ks > SP_KS_MAX) ks = SP_KS_MAX;
+  if (ks > chunks) ks = chunks;
+  const int per = (chunks + ks - 1) / ks;
+  ga.ks_cols = per * GK;
+  ga.KS = (chunks + per - 1) / per;
+  split_gram_kernel<<<dim3(ntiles, ga.KS), 256, 0, st>>>(ga);
+  TRMPS_LAUNCH_OK("split_gram_kernel");
+  // 2. Cholesky
+  CholArgs ca;
+  ca.G = w.G; ca.Rd = w.Rd; ca.Rf = w.Rf; ca.R = R; ca.d_near = g.d_near; ca.scale = w.scale; ca.rowmap = w.rowmap; ca.dbg = s->work + lay.red + 8;
+  {
+    const size_t smem = (size_t)(2 * CW * SP_NMAX + CW * CT) * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_done = true;
+    }
+    split_chol_kernel<<<1, CT, smem, st>>>(ca);
+  }
+  TRMPS_LAUNCH_OK("split_chol_kernel");
+  // 3. Jacobi in one cluster
+  JacArgs ja;
+  ja.Rf = w.Rf; ja.R = R; ja.rowmap = w.rowmap; ja.d_near = g.d_near; ja.X = w.X; ja.sig = w.sig; ja.iscal = s->iwork;
+  ja.tol = 5.9604645e-8f * sqrtf((float)R);
+  ja.stop = 3e-4f;
+  ja.max_sweeps = opt->max_svd_sweeps > 0 ? (opt->max_svd_sweeps < 40 ? opt->max_svd_sweeps : 40) : 40;
+  const int pairs = ((R + JB - 1) / JB + 1) / 2;
+  ja.csize = pairs <= 1 ? 1 : pairs <= 2 ? 2 : pairs <= 4 ? 4 : 8;
+  ja.dbg = s->work + lay.red;
+  {
+    const size_t smem = (size_t)2 * 2 * JB * JLD * sizeof(float);
+    const bool wide = R > 128;
+    static bool attr_done = false;
+    if (!attr_done) {
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ja.csize);
+    cfg.blockDim = dim3(JT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = ja.csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (wide) TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_kernel<true>, ja));
+    else TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_kernel<false>, ja));
+    count_launch();
+  }
+  // 4. ranking
+  RankArgs ra;
+  ra.sig = w.sig; ra.scale = w.scale; ra.nslots = ja.csize * 2 * JB; ra.R = R; ra.d_near = g.d_near; ra.d_far = g.d_far;
+  ra.ncol_blocks = single ? L : 2 * L;
+  ra.sv = s->work + lay.sv;
+  ra.order = reinterpret_cast<int32_t*>(s->work + lay.sv + R);
+  ra.iscal = s->iwork;
+  ra.dim_out = s->dims + (g.dir > 0 ? g.near_site + 1 : g.near_site);
+  ra.min_sv = opt->min_singular_value;
+  ra.max_size = opt->max_size < Ds ? opt->max_size : Ds;
+  ra.min_size = opt->min_size > 0 ? opt->min_size : 3;
+  split_rank_kernel<<<1, SP_NMAX, 0, st>>>(ra);
+  TRMPS_LAUNCH_OK("split_rank_kernel");
+  // 5. projection + scatter
+  ProjArgs pa;
+  pa.M = M; pa.X = ja.X; pa.order = ra.order; pa.iscal = s->iwork; pa.d_near = g.d_near;
+  pa.R = R; pa.Cc = Cc; pa.Ds = Ds; pa.L = L; pa.dir = g.dir;
+  pa.node = s->nodes + (size_t)g.near_site * 2 * Ds * Ds;
+  pa.special = special_out ? special_out : s->special;
+  pa.ncol_tiles = (Cc + PT - 1) / PT;
+  const int qtiles = (Ds + PT - 1) / PT;
+  split_project_kernel<<<dim3(pa.ncol_tiles + 8, qtiles), 256, 0, st>>>(pa);
+  TRMPS_LAUNCH_OK("split_project_kernel");
+  return TRMPS_OK;
+}
+
+}  // namespace trmps

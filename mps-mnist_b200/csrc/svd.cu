@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 #include <type_traits>
 #include "common.cuh"
+#include "svd_common.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -33,7 +34,6 @@ struct SvdArgs {
   float tol; int max_sweeps; int keep; float* dbg;   // keep: rows that can survive the truncation (max_size); dbg: 8 floats, phase cycle counters of CTA 0 (load, gram, rotate, replay, store, grid sync)
 };
 
-__device__ __forceinline__ int compact_to_row(int p, int dn, int Ds) { return (p / dn) * Ds + (p % dn); }
 
 // squared norms of the active rows (one warp per row)
 __global__ void svd_norms_kernel(SvdArgs a) {
@@ -83,9 +83,6 @@ __global__ void svd_init_ut_kernel(SvdArgs a) {
   if (p < Ra) a.Ut[(size_t)p * a.R + a.rowmap[p]] = 1.f;
 }
 
-// round-robin pairing of n players (n even): pair #j in step s
-__host__ __device__ constexpr int rr_first(int n, int s, int j) { return j == 0 ? n - 1 : (s + j) % (n - 1); }
-__host__ __device__ constexpr int rr_second(int n, int s, int j) { return j == 0 ? s : (s + n - 1 - j) % (n - 1); }
 
 // per-warp partial sums of K per-thread values -> part[warp][k]  (first stage of a deterministic block reduction).
 // Transposing butterfly: each exchange halves the number of live values, so K values cost K-1+log2(32/K)
@@ -356,37 +353,7 @@ __device__ __forceinline__ void pair_of_row(int all, int step, int row, int& x, 
   else { pidx = (NR - 1) - j; y = row; x = (step + pidx) % (NR - 1); }
 }
 
-__device__ __forceinline__ float rsqrt_fast(float x) {      // one MUFU.RSQ, no denormal fix-up (callers keep x in range)
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
-// rotation that annihilates the (x,y) entry of a 2x2 Gram [[al, ga],[ga, be]]: x' = c x - s y, y' = s x + c y.
-// Half-angle form on the NORMALISED Gram (divide by sqrt(al be): no exponent juggling, nothing can over- or
-// underflow while the pair is rotated at all): cos 2t = |d| / hyp, sin 2t = sgn * 2|g| / hyp with
-// d = (be - al) / sqrt(al be), g = ga / sqrt(al be), c = sqrt((1 + cos 2t)/2), s = sin 2t / (2c).
-// The dependent chain is rsqrt -> 2 mul -> fma -> rsqrt -> mul -> fma -> rsqrt -> 2 mul (~110 cycles; the previous
-// form with exponent arithmetic and IEEE-range rsqrtf took 250, tools/probe/rot_probe.cu).
-__device__ __forceinline__ bool rotation_params(float al, float be, float ga, float tol, float& c, float& s, float& tau, float& relg) {
-  const float big = fmaxf(al, be), small = fminf(al, be);
-  const float rr = rsqrt_fast(al) * rsqrt_fast(be);
-  const float g = ga * rr;                                      // cosine of the angle between the rows
-  relg = fabsf(g);
-  const bool rot = small > 1e-30f && small > 1e-24f * big && relg > tol;
-  const float d = (be - al) * rr;                               // |d| <= sqrt(big / small) <= 1e12 when rot
-  const float rh = rsqrt_fast(fmaf(d, d, 4.f * g * g));        // 1 / hyp
-  const float c2 = fabsf(d) * rh;                               // cos 2t  (>= 0)
-  const float x = fmaf(0.5f, c2, 0.5f);                         // cos^2 t in [0.5, 1]
-  const float rc = rsqrt_fast(x);                               // 1 / c
-  const float cc = x * rc;
-  const float ss = ((d >= 0.f) ? g : -g) * rh * rc;             // sin 2t / (2 c), sin 2t = sgn * 2 g / hyp
-  c = rot ? cc : 1.f;
-  s = rot ? ss : 0.f;
-  tau = rot ? __fdividef(ss, 1.f + cc) : 0.f;
-  relg = rot ? relg : 0.f;
-  return rot;
-}
 
 template <int SLOTS>
 __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArgs ca) {
@@ -807,6 +774,7 @@ static int launch_jacobi(SvdArgs& a, int ncta, cudaStream_t st) {
 int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, cudaStream_t st,
               float* special_out, bool single) {
   const int Ds = s->Ds, L = s->L, R = 2 * Ds, Cc = 2 * L * Ds;
+  if (opt->split_impl == 0 && split_factor_supported(R)) return split_factor(s, lay, g, opt, st, special_out, single);
   const int blk = lay.svd_block;
   if (blk == 0) {
     set_error("svd: bond stride Ds=%d (R=%d, Cc=%d) is outside the supported range (Cc <= 5120, R <= 512)", Ds, R, Cc);
@@ -821,7 +789,7 @@ int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, 
   a.tol = 5.9604645e-8f * sqrtf((float)Cc);
   a.dbg = s->work + lay.red;
   a.keep = opt->max_size < Ds ? opt->max_size : Ds;
-  a.max_sweeps = opt->max_svd_sweeps > 0 ? (opt->max_svd_sweeps < 30 ? opt->max_svd_sweeps : 30) : 30;
+  a.max_sweeps = opt->max_svd_sweeps > 0 ? (opt->max_svd_sweeps < 40 ? opt->max_svd_sweeps : 40) : 40;
   svd_norms_kernel<<<(R * 32 + 255) / 256, 256, 0, st>>>(a);
   TRMPS_LAUNCH_OK("svd_norms_kernel");
   svd_init_kernel<<<32, 256, 0, st>>>(a);
@@ -842,21 +810,18 @@ int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, 
     const int nbk = (R + CL_NR / 2 - 1) / (CL_NR / 2);
     ca.wtop = ca.flags + (nbk + 1) * CL_SIZE;
     const int ncl = ((nbk + (nbk & 1)) / 2) > 1 ? (nbk + (nbk & 1)) / 2 : 1;
-    static bool cluster_ok = true;
-    if (cluster_ok && slots <= 4 && ca.ucols_per_cta <= CL_MAXU && (nbk + 1) * CL_SIZE <= 2048) {
+    if (slots <= 4 && ca.ucols_per_cta <= CL_MAXU && (nbk + 1) * CL_SIZE <= 2048) {
       svd_zero_flags_kernel<<<((nbk + 1) * CL_SIZE + 40 + 255) / 256, 256, 0, st>>>(ca.flags, (nbk + 1) * CL_SIZE + 40);
       TRMPS_LAUNCH_OK("svd_zero_flags_kernel");
+      // a refused cluster + cooperative launch is an error, not a reason to switch kernels: the single-CTA kernel
+      // rotates in another order, so a rank that fell back alone would leave the replicated MPS of a data-parallel job
       cudaError_t e = slots <= 1 ? launch_jacobi_cluster<1>(ca, ncl, st)
                     : slots <= 2 ? launch_jacobi_cluster<2>(ca, ncl, st)
                     : slots <= 3 ? launch_jacobi_cluster<3>(ca, ncl, st)
                                  : launch_jacobi_cluster<4>(ca, ncl, st);
-      if (e == cudaSuccess) {
-        count_launch();
-        done = true;
-      } else {
-        (void)cudaGetLastError();      // cluster + cooperative launch refused: use the single-CTA kernel from now on
-        cluster_ok = false;
-      }
+      if (e != cudaSuccess) return cuda_fail(e, "svd_jacobi_cluster_kernel (cluster + cooperative launch)");
+      count_launch();
+      done = true;
     }
   }
   if (!done) {

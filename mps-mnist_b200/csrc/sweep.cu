@@ -55,16 +55,12 @@ static int g_fwd_impl = 0;    // same for the forward contraction
 static int g_chain_impl = 0;  // 0 = fused tcgen05 chain for inference when Ds <= 32, 1 = per-site FP32 SIMT steps
 int option_value(int option) { return option == 0 ? g_grad_impl : option == 1 ? g_fwd_impl : g_chain_impl; }
 
-static int g_sm_count = 0;
+// SM count of the CURRENT device (ranks above 0 of a multi-GPU process group run on other devices; the attribute query
+// is a host-side table lookup)
 static int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      g_sm_count = n;
-    else
-      g_sm_count = 148;
-  }
-  return g_sm_count;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) return n;
+  return 148;
 }
 
 // ------------------------------------------------------------------------------------------ layout
@@ -104,8 +100,6 @@ static int compute_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, int32_t s
     if (eff > best_eff + 1e-9) { best_eff = eff; best = ns; }
     if (eff >= 0.9) { best = ns; break; }
   }
-  const bool fwd_tc = g_fwd_impl != 1 && forward_tc_supported(Ds, L, 2);
-  if (fwd_tc) best = 1;      // the tensor-core forward writes complete logits
   int64_t off = 0;
   o->bondM = off; off += a4(RC);
   o->gradM = off; off += a4(RC + TRMPS_S_COUNT);
@@ -127,6 +121,7 @@ static int compute_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, int32_t s
   o->red = off; off += a4(rr * 32);
   o->scal = off; off += a4(2 * TRMPS_S_COUNT);
   o->bimg = off; off += a4(forward_tc_supported(Ds, L, 2) ? forward_tc_image_floats(Ds, L) : 0);
+  o->split_ws = off; off += a4(split_factor_supported((int)R) ? split_ws_floats((int)R) : 0);
   o->total = off;
   o->gsplit = (int32_t)gs;
   o->nsplit = best;
@@ -158,6 +153,12 @@ BondGeom bond_geom(const trmps_sweep* s, int site, int dir) {
     g.d_far = s->dims + site - 1;
   }
   return g;
+}
+
+// column split of the forward actually in use: the tensor-core forward writes complete logits (one part); the layout
+// always reserves the parts of the FP32 SIMT kernel, so switching kernels with trmps_set_option never moves a buffer
+static int eff_nsplit(const trmps_sweep* s, const trmps_layout& lay) {
+  return (g_fwd_impl != 1 && forward_tc_supported(s->Ds, s->L, 2)) ? 1 : lay.nsplit;
 }
 
 static int check_sweep(const trmps_sweep* s, const char* who) {
@@ -242,7 +243,7 @@ static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const Bond
   float* w = s->work;
   const bool hess = opt->use_hessian && s->loss_kind == TRMPS_LOSS_SOFTMAX_XENT;   // baseoptimizer.py:32-35
   LossArgs la;
-  la.fpart = w + lay.fpart; la.nsplit = lay.nsplit; la.f0 = w + lay.f0; la.labels = s->labels;
+  la.fpart = w + lay.fpart; la.nsplit = eff_nsplit(s, lay); la.f0 = w + lay.f0; la.labels = s->labels;
   la.phi_far = w + lay.phi2 + 2 * s->B; la.resid = w + lay.resid; la.sres = w + lay.sres;
   la.hres = hess ? w + lay.hres : nullptr; la.red = w + lay.red; la.B = s->B; la.L = L; la.loss_kind = s->loss_kind;
   la.from_parts = from_parts;
@@ -304,7 +305,7 @@ static int do_update_bond(const trmps_sweep* s, const trmps_layout& lay, const B
     if ((rc = do_gradient(s, lay, g, opt, u == 0, st))) return rc;
     if ((rc = do_forward(s, lay, g, delta, st))) return rc;         // f(delta): serves every Armijo trial
     ArmijoArgs aa;
-    aa.f0 = w + lay.f0; aa.fdpart = w + lay.fpart; aa.nsplit = lay.nsplit; aa.fd = w + lay.fd; aa.labels = s->labels;
+    aa.f0 = w + lay.f0; aa.fdpart = w + lay.fpart; aa.nsplit = eff_nsplit(s, lay); aa.fd = w + lay.fd; aa.labels = s->labels;
     aa.red = w + lay.red; aa.B = s->B; aa.L = L; aa.loss_kind = s->loss_kind; aa.lr = opt->lr;
     ProfScope ps(PROF_SCALAR, st);
     if ((rc = launch_armijo(aa, st))) return rc;
@@ -533,6 +534,10 @@ extern "C" int trmps_sweep_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, i
   {                                                                                 \
     int _rc = compute_layout((s)->N, (s)->B, (s)->L, (s)->Ds, sm_count(), &lay);    \
     if (_rc) return _rc;                                                            \
+    if ((s)->work_floats < lay.total) {                                             \
+      set_error("%s: work buffer holds %lld floats, the layout needs %lld (trmps_sweep_layout)", who, (long long)(s)->work_floats, (long long)lay.total); \
+      return TRMPS_E_ARG;                                                           \
+    }                                                                               \
   }
 
 extern "C" int trmps_sweep_init_env(const trmps_sweep* s, int32_t loc, void* stream) {
@@ -595,7 +600,7 @@ extern "C" int trmps_bond_forward(const trmps_sweep* s, int32_t site, int32_t di
   const float* M = s->work + (use_delta == 2 ? lay.deltaM : use_delta == 1 ? lay.gradM : lay.bondM);
   if ((rc = do_forward(s, lay, g, M, st))) return rc;
   float* dst = s->work + (use_delta ? lay.fd : lay.f0);
-  return launch_sum_round_logits(s->work + lay.fpart, lay.nsplit, s->B, s->L, 0, dst, st);
+  return launch_sum_round_logits(s->work + lay.fpart, eff_nsplit(s, lay), s->B, s->L, 0, dst, st);
 }
 
 extern "C" int trmps_bond_gradient(const trmps_sweep* s, int32_t site, int32_t dir, const trmps_opt* opt, void* stream) {

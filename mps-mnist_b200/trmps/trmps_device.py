@@ -221,7 +221,7 @@ class SweepState(object):
                                feat=self.feat.data_ptr(), labels=self.labels.data_ptr(), nodes=self.slots.data_ptr(),
                                special=self.special.data_ptr(), dims=self.dims.data_ptr(), envL=self.envL.data_ptr(),
                                envR=self.envR.data_ptr(), work=self.work.data_ptr(), iwork=self.iwork.data_ptr(),
-                               comm=comm)
+                               comm=comm, work_floats=int(self.work.numel()))
 
     # ---- views into the library-defined work buffer -------------------------------------------
     @property
@@ -321,8 +321,9 @@ class SweepState(object):
 
 
 def make_opt(lr, max_size, reg=1e-3, armijo_coeff=1e-4, min_singular_value=1e-4, updates_per_step=1,
-             use_hessian=False, min_size=3, max_svd_sweeps=0, single_site=False):
+             use_hessian=False, min_size=3, max_svd_sweeps=0, single_site=False, split_impl=0):
     return nat.Opt(lr=float(lr), reg=float(reg), armijo_coeff=float(armijo_coeff),
                    min_singular_value=float(min_singular_value), max_size=int(max_size), min_size=int(min_size),
                    updates_per_step=int(updates_per_step), use_hessian=int(bool(use_hessian)),
-                   max_svd_sweeps=int(max_svd_sweeps), single_site=int(bool(single_site)))
+                   max_svd_sweeps=int(max_svd_sweeps), single_site=int(bool(single_site)),
+                   split_impl=int(split_impl), reserved=0)

@@ -27,13 +27,14 @@ class Opt(C.Structure):
     _fields_ = [("lr", C.c_float), ("reg", C.c_float), ("armijo_coeff", C.c_float),
                 ("min_singular_value", C.c_float), ("max_size", C.c_int32), ("min_size", C.c_int32),
                 ("updates_per_step", C.c_int32), ("use_hessian", C.c_int32),
-                ("max_svd_sweeps", C.c_int32), ("single_site", C.c_int32)]
+                ("max_svd_sweeps", C.c_int32), ("single_site", C.c_int32),
+                ("split_impl", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Layout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
                 ("bondM", "gradM", "deltaM", "hessM", "gpart", "f0", "fd", "fpart", "resid", "sres", "hres",
-                 "phi2", "Ut", "sv", "red", "scal", "bimg", "total")] + \
+                 "phi2", "Ut", "sv", "red", "scal", "bimg", "split_ws", "total")] + \
                [(n, C.c_int32) for n in ("gsplit", "nsplit", "red_rows", "svd_block", "gsplit_tc", "reserved0")]
 
 
@@ -43,7 +44,7 @@ class Sweep(C.Structure):
                 ("feature_map", C.c_int32), ("loss_kind", C.c_int32),
                 ("feat", C.c_void_p), ("labels", C.c_void_p), ("nodes", C.c_void_p), ("special", C.c_void_p),
                 ("dims", C.c_void_p), ("envL", C.c_void_p), ("envR", C.c_void_p), ("work", C.c_void_p),
-                ("iwork", C.c_void_p), ("comm", C.c_void_p)]
+                ("iwork", C.c_void_p), ("comm", C.c_void_p), ("work_floats", C.c_int64)]
 
 
 class PredictDesc(C.Structure):

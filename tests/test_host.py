@@ -34,9 +34,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_the_header_layout():
     import ctypes as C
-    assert C.sizeof(nat.Opt) == 40
-    assert C.sizeof(nat.Layout) == 18 * 8 + 6 * 4
-    assert C.sizeof(nat.Sweep) == 4 * 4 + 2 * 8 + 2 * 4 + 10 * 8
+    assert C.sizeof(nat.Opt) == 48
+    assert C.sizeof(nat.Layout) == 19 * 8 + 6 * 4
+    assert C.sizeof(nat.Sweep) == 4 * 4 + 2 * 8 + 2 * 4 + 10 * 8 + 8
     assert C.sizeof(nat.PredictDesc) == 4 * 4 + 8 + 4 * 4 + 6 * 8
 
 
@@ -65,7 +65,7 @@ def test_layout_arithmetic():
     assert lay.gsplit == 7 and lay.gsplit_tc == 14 and lay.svd_block == 8 and 1 <= lay.nsplit <= 8
     assert lay.total - lay.bimg >= 30 * 8 * 2 * 16 * 160      # hi/lo bond images of the tensor-core forward
     assert lay.total * 4 < 200e6
-    for off in ("bondM", "gradM", "deltaM", "hessM", "gpart", "f0", "fd", "fpart", "resid", "sres", "hres", "phi2", "Ut", "sv", "red", "scal", "bimg"):
+    for off in ("bondM", "gradM", "deltaM", "hessM", "gpart", "f0", "fd", "fpart", "resid", "sres", "hres", "phi2", "Ut", "sv", "red", "scal", "bimg", "split_ws"):
         assert getattr(lay, off) % 4 == 0
     with pytest.raises(RuntimeError):
         nat.sweep_layout(10, 100, 10, 20, 148)      # Ds must be a multiple of 8
