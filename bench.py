@@ -193,7 +193,7 @@ def cpu_sweep_rate(cfg, B_s, bonds, lr, seed=100):
     pix, lab = synthetic_pixels(N, B_s, L_OUT, seed)
     phi = o.feature_map(pix, fm)
     nodes, _ = benchmark_mps(cfg, loc, lambda nd, px: o.predict(nd, loc, o.feature_map(px, fm), L_OUT),
-                             lambda: o.initial_nodes(N, 2, L_OUT, loc=loc))
+                             lambda: o.initial_nodes(N, 2, L_OUT, loc=loc)[0])
     p = o.SweepParams(max_size=D, min_singular_value=0.0)
     bonds = min(bonds, N - 1 - loc)
     t0 = time.perf_counter()

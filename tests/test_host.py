@@ -166,3 +166,42 @@ def test_bench_reference_arm_prints_contract_json():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "sweep_images_bonds_per_sec" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_reference_checkpoint_fixture_parses_with_boundary_one():
+    """The one trained-weights file the reference ships (trmps/generation/MPSconfig) was written by its generation module:
+    a shortMPS whose outer bonds are 1, not 2L.  Its bytes follow MPS.save (mps.py:126-160): flag, int16 N / loc / d / L, N
+    int16 right-bond dimensions, float32 C-order tensors.  Parsed here with boundary 1 (our from_file keeps the reference's
+    boundary 2L, mps.py:80-124, under which the reference's own loader cannot read this file either): the byte count has to
+    come out exactly, and the weights must be the mixed-canonical MPS SURVEY.md section 2 describes."""
+    path = "/root/reference/trmps/generation/MPSconfig"
+    if not os.path.isfile(path):
+        pytest.skip("reference tree not present (GPU box)")
+    raw = open(path, "rb").read()
+    assert len(raw) == 731041
+    be = lambda a, b: int.from_bytes(raw[a:b], "big")
+    assert raw[0] == 1
+    N, loc, d, L = be(1, 3), be(3, 5), be(5, 7), be(7, 9)
+    assert (N, loc, d, L) == (196, 91, 2, 11)
+    dims = [be(9 + 2 * i, 11 + 2 * i) for i in range(N)]
+    assert dims[-1] == 1 and max(dims) == 40 and dims[0] == 2
+    pos, nodes = 9 + 2 * N, []
+    for i in range(N):
+        dl, dr = (1 if i == 0 else dims[i - 1]), dims[i]
+        n = dl * dr * d * (L if i == loc else 1)
+        shape = (L, d, dl, dr) if i == loc else (d, dl, dr)
+        nodes.append(np.frombuffer(raw[pos:pos + 4 * n], dtype="<f4").astype(np.float64).reshape(shape))     # the tensors are native (little-endian) float32, only the header is big-endian
+        pos += 4 * n
+    assert pos == len(raw)                                   # every byte accounted for
+    for i, w in enumerate(nodes):
+        if i < loc:        # left-canonical: sum_{m,a} A[m,a,b] A[m,a,b'] = delta
+            g = np.einsum('mab,mac->bc', w, w)
+        elif i > loc:      # right-canonical: sum_{m,b} A[m,a,b] A[m,a',b] = delta
+            g = np.einsum('mab,mcb->ac', w, w)
+        else:
+            continue
+        assert np.abs(g - np.eye(g.shape[0])).max() < 2e-5, i
+    # the same bytes go through our writer unchanged (format parity, whatever the boundary)
+    out = (True).to_bytes(1, "big") + b"".join(int(v).to_bytes(2, "big") for v in (N, loc, d, L)) + b"".join(int(v).to_bytes(2, "big") for v in dims)
+    out += b"".join(np.ascontiguousarray(w, dtype="<f4").tobytes() for w in nodes)
+    assert out == raw
