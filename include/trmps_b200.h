@@ -126,6 +126,7 @@ typedef struct {
   int64_t scal;                          /* TRMPS_S_COUNT floats */
   int64_t bimg;                          /* TF32 hi/lo shared-memory images of the bond for the tensor-core forward */
   int64_t split_ws;                      /* FP64 Gram partials, Gram matrix, Cholesky factor and the rotated factor of the split */
+  int64_t env_img;                       /* fp16 hi/lo images of up to N node matrices for the tensor-core environment chain */
   int64_t total;                         /* floats the caller must allocate for `work` */
   int32_t gsplit, nsplit;                /* split-K factor of the gradient, column split of the forward */
   int32_t red_rows, svd_block;           /* rows of `red`; rows per Jacobi block */
@@ -175,7 +176,10 @@ int         trmps_device_check(int device);             /* TRMPS_OK if `device` 
 int         trmps_set_option(int32_t option, int32_t value); /* option 0: gradient kernel, 1: forward kernel, 2: inference chain; value 0 = tcgen05 (default), 1 = FP32 SIMT;
                                                             option 2 value 2: fused tensor-core chain even for chains so long that its accumulated
                                                             rounding bias is estimated above 9e-5 (value 0 then uses the per-site FP32 path);
-                                                            option 3: tile shape of the flat datasource kernel (development switch, 0 = default) */
+                                                            option 3: tile shape of the flat datasource kernel (development switch, 0 = default);
+                                                            option 4: environment chain of the sweep (initial build and the advance after every
+                                                            split): 0 = tcgen05 (the inference chain started from / writing to HBM) while the
+                                                            chain's rounding-bias estimate stays below 9e-5, 1 = FP32 SIMT steps */
 int64_t     trmps_launch_count(void);                   /* kernels launched by this library so far (process-wide) */
 
 /* optional device-side timing of the kernels a sweep launches (CUDA events on the caller's stream; replaces the

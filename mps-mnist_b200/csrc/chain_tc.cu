@@ -228,6 +228,9 @@ __device__ float g_chain_dbg[64];     // [0..7] phase counters, [16..63] event t
 struct ChainArgs {
   const float* feat; int fm; int64_t B; int Ds, L; int first, dir, nsteps; int start_kind;   // start_kind 0: [0_L,1_L], 1: [1_L,0_L]
   const uint8_t* img; const int32_t* exps; float* out;      // out: (B, Ds) final environment
+  const float* in;          // start_kind 2: the chain starts from this environment (B, Ds) in HBM instead of a boundary vector
+  float* out_all;           // not null: the environment after step s (s < nsteps - 1) is also written to out_all + s * out_stride
+  int64_t out_stride;       //           (training: the cached environments C1s / C2s, optimizer.py:49-87)
   int dbg;       // development: 1 = epilogue skips TMEM reads and A-tile stores, 2 = loader skips the copies (rate experiments; results invalid)
 };
 
@@ -415,8 +418,48 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
       tc_fence_before();
       mbar_arrive(&a_ready[k]);
     };
-    // start vector (mps.py:446-466): exactly representable, row maximum 1 -> shift by TROW
-    if (nsteps > 0) {
+    // environment after a step in fp32 (training caches): 32 of my columns, true value = v * 2^e
+    auto emit32 = [&](const float (&v)[32], int j0, int e, float* base) {
+      if (!live) return;
+      float* o = base + t * a.Ds + j0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        if (j0 + j < a.Ds)
+          *reinterpret_cast<float4*>(o + j) = make_float4(scale_pow2(v[j], e), scale_pow2(v[j + 1], e), scale_pow2(v[j + 2], e), scale_pow2(v[j + 3], e));
+    };
+    if (nsteps > 0 && a.start_kind == 2) {
+      // start from an environment in HBM (one training step of the chain, _find_C1/_find_C2 baseoptimizer.py:160-201):
+      // my JW columns of my row, row maximum over the warpgroups of the tile, exact power-of-two shift into the fp16 window
+      float v[JW / 32][32];
+      float mx = 0.f;
+#pragma unroll
+      for (int c = 0; c < JW / 32; ++c) {
+        const int j0 = g * JW + c * 32;
+        const float* src = a.in + t * a.Ds + j0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live && j0 + j < a.Ds) x = __ldg(reinterpret_cast<const float4*>(src + j));
+          v[c][j] = x.x; v[c][j + 1] = x.y; v[c][j + 2] = x.z; v[c][j + 3] = x.w;
+          mx = fmaxf(mx, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+        }
+      }
+      if (WG > 1) {
+        mx_x[(k * WG + g) * CH_TM + row] = mx;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "r"(WG * 128) : "memory");
+#pragma unroll
+        for (int o = 0; o < WG; ++o) mx = fmaxf(mx, mx_x[(k * WG + o) * CH_TM + row]);
+      }
+      const bool valid = mx > 0.f && mx < 3.0e38f;
+      const int sh = valid ? max(-120, min(120, CH_TROW - exponent_of(mx))) : 0;
+      const float sc = pow2f(sh);
+#pragma unroll
+      for (int c = 0; c < JW / 32; ++c) store_chunk32(v[c], g * JW + c * 32, sc);
+      if (WG > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "r"(WG * 128) : "memory");      // mx_x is reused in the first step
+      E = -sh;
+      publish();
+    } else if (nsteps > 0) {
+      // start vector (mps.py:446-466): exactly representable, row maximum 1 -> shift by TROW
 #pragma unroll 1
       for (int c = 0; c < JW / 32; ++c) {
         float v[32];
@@ -509,6 +552,7 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
 #pragma unroll
             for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fabsf(v[j]));
             store_chunk32(v, g * JW + c * 32, 1.f);
+            if (a.out_all) emit32(v, g * JW + c * 32, E + fs_exp - sh, a.out_all + (int64_t)s * a.out_stride);
           }
         }
         if (WG > 1) {
@@ -530,6 +574,7 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
             float v[32];
             chunk(c, v);
             store_chunk32(v, g * JW + c * 32, sc);
+            if (a.out_all) emit32(v, g * JW + c * 32, E + fs_exp, a.out_all + (int64_t)s * a.out_stride);
           }
           pos = ex + sh;
         }
@@ -605,18 +650,21 @@ int64_t chain_tc_image_floats(int Ds, int nsteps) {
   return (int64_t)nsteps * (chain_site_bytes(Ds) / 4) + (((int64_t)nsteps + 3) / 4) * 4 + 8;
 }
 
-// runs `nsteps` chain steps starting at site `first` in direction dir from the boundary vector; writes the final
-// environment (B x Ds).  img: 16-byte aligned scratch of chain_tc_image_floats(Ds, nsteps) floats.
+// runs `nsteps` chain steps starting at site `first` in direction dir from the boundary vector (start_kind 0 / 1) or from the
+// environment in_env (start_kind 2); writes the final environment (B x Ds) to `out` and, when out_all is given, the
+// environment after step s < nsteps - 1 to out_all + s * out_stride.  img: 16-byte aligned scratch of
+// chain_tc_image_floats(Ds, nsteps) floats.
 int launch_chain_tc(const float* feat, int fm, int64_t B, int Ds, int L, const float* nodes, int first, int dir, int nsteps,
-                    int start_kind, float* img, float* out, cudaStream_t st) {
+                    int start_kind, float* img, float* out, cudaStream_t st, const float* in_env, float* out_all, int64_t out_stride) {
   if (B <= 0) return TRMPS_OK;
   if (!chain_tc_supported(Ds)) {
     set_error("chain_tc: Ds=%d not supported (<= 128, multiple of 4)", Ds);
     return TRMPS_E_ARG;
   }
+  if (start_kind == 2 && !in_env) { set_error("chain_tc: start_kind 2 needs an input environment"); return TRMPS_E_ARG; }
   ChainArgs a;
   a.feat = feat; a.fm = fm; a.B = B; a.Ds = Ds; a.L = L; a.first = first; a.dir = dir; a.nsteps = nsteps;
-  a.start_kind = start_kind; a.out = out;
+  a.start_kind = start_kind; a.out = out; a.in = in_env; a.out_all = out_all; a.out_stride = out_stride;
   static const int dbg_mode = getenv("TRMPS_CHAIN_DEBUG") ? atoi(getenv("TRMPS_CHAIN_DEBUG")) : 0;
   a.dbg = dbg_mode;
   uint8_t* image = reinterpret_cast<uint8_t*>(img);

@@ -173,7 +173,8 @@ double chain_tc_bias_estimate(int Ds, int nsites);
 int chain_tc_debug(float* out64);
 int64_t chain_tc_image_floats(int Ds, int nsteps);
 int launch_chain_tc(const float* feat, int fm, int64_t B, int Ds, int L, const float* nodes, int first, int dir, int nsteps,
-                    int start_kind, float* img, float* out, cudaStream_t st);
+                    int start_kind, float* img, float* out, cudaStream_t st, const float* in_env = nullptr, float* out_all = nullptr,
+                    int64_t out_stride = 0);
 int option_value(int option);
 bool forward_tc_supported(int Ds, int L, int nd);
 int64_t forward_tc_image_floats(int Ds, int L);

@@ -53,6 +53,7 @@ ProfScope::~ProfScope() {
 static int g_grad_impl = 0;   // 0 = tcgen05 3xTF32, 1 = FP32 SIMT
 static int g_fwd_impl = 0;    // same for the forward contraction
 static int g_chain_impl = 0;  // 0 = fused tcgen05 chain for inference when Ds <= 32, 1 = per-site FP32 SIMT steps
+static int g_env_impl = 0;    // environments of the sweep: 0 = tcgen05 chain from / to HBM, 1 = per-site FP32 SIMT steps
 int option_value(int option) { return option == 0 ? g_grad_impl : option == 1 ? g_fwd_impl : g_chain_impl; }
 
 // SM count of the CURRENT device (ranks above 0 of a multi-GPU process group run on other devices; the attribute query
@@ -67,7 +68,6 @@ static int sm_count() {
 static int64_t a4(int64_t x) { return (x + 3) / 4 * 4; }
 
 static int compute_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, int32_t sms, trmps_layout* o) {
-  (void)N;
   if (B < 0 || L < 1 || L > TRMPS_LMAX || Ds < 2 * L || Ds % 8 != 0) {
     set_error("layout: unsupported shape (need 1<=L<=16, Ds%%8==0, Ds>=2L); got L=%d Ds=%d", L, Ds);
     return TRMPS_E_ARG;
@@ -122,6 +122,7 @@ static int compute_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, int32_t s
   o->scal = off; off += a4(2 * TRMPS_S_COUNT);
   o->bimg = off; off += a4(forward_tc_supported(Ds, L, 2) ? forward_tc_image_floats(Ds, L) : 0);
   o->split_ws = off; off += a4(split_factor_supported((int)R) ? split_ws_floats((int)R) : 0);
+  o->env_img = off; off += a4(chain_tc_supported(Ds) ? chain_tc_image_floats(Ds, N > 1 ? N : 1) : 0);
   o->total = off;
   o->gsplit = (int32_t)gs;
   o->nsplit = best;
@@ -317,18 +318,24 @@ static int do_update_bond(const trmps_sweep* s, const trmps_layout& lay, const B
   return TRMPS_OK;
 }
 
+// the sweep's environments run on the tensor cores (the inference chain started from / writing to HBM) while the rounding
+// bias of the fused chain over the whole MPS stays inside the tolerance (chain_tc.cu, "Order of accumulation")
+static bool env_on_tensor_cores(const trmps_sweep* s) {
+  return g_env_impl == 0 && chain_tc_supported(s->Ds) && chain_tc_bias_estimate(s->Ds, s->N) <= 9e-5;
+}
+
 // environment advance over the site that just received its isometry (optimizer.py:187-190 / :132-135)
-static int do_env_advance(const trmps_sweep* s, int site, int dir, cudaStream_t st) {
+static int do_env_advance(const trmps_sweep* s, const trmps_layout& lay, int site, int dir, cudaStream_t st) {
   ProfScope ps_env(PROF_ENV, st);
   const int Ds = s->Ds;
   const int64_t stride = s->B * (int64_t)Ds;
+  const float* in_env = dir > 0 ? s->envL + stride * site : s->envR + stride * site;
+  float* out_env = dir > 0 ? s->envL + stride * (site + 1) : s->envR + stride * (site - 1);
+  if (env_on_tensor_cores(s))
+    return launch_chain_tc(s->feat, s->feature_map, s->B, Ds, s->L, s->nodes, site, dir, 1, 2, s->work + lay.env_img, out_env, st, in_env);
   const float* feat_site = s->feat + feat_site_offset(s->feature_map, s->B, site);
   const float* node = s->nodes + (size_t)site * 2 * Ds * Ds;
-  if (dir > 0)
-    return launch_env_step(feat_site, s->feature_map, s->B, Ds, +1, s->envL + stride * site, node, s->dims + site,
-                           s->envL + stride * (site + 1), st);
-  return launch_env_step(feat_site, s->feature_map, s->B, Ds, -1, s->envR + stride * site, node, s->dims + site + 1,
-                         s->envR + stride * (site - 1), st);
+  return launch_env_step(feat_site, s->feature_map, s->B, Ds, dir, in_env, node, dir > 0 ? s->dims + site : s->dims + site + 1, out_env, st);
 }
 
 static int do_bond_step(const trmps_sweep* s, const trmps_layout& lay, int site, int dir, const trmps_opt* opt, cudaStream_t st) {
@@ -341,7 +348,7 @@ static int do_bond_step(const trmps_sweep* s, const trmps_layout& lay, int site,
     ProfScope ps(PROF_SVD, st);
     if ((rc = svd_split(s, lay, g, opt, st))) return rc;
   }
-  return do_env_advance(s, site, dir, st);
+  return do_env_advance(s, lay, site, dir, st);
 }
 
 // single-site update (singlesiteOptimizer.py:49-138): optimise the special node at `site`, split it into the
@@ -371,27 +378,38 @@ static int do_site_step(const trmps_sweep* s, const trmps_layout& lay, int site,
     ProfScope ps(PROF_MERGE, st);
     if ((rc = launch_site_absorb(tmp, s->nodes + (size_t)(site + dir) * 2 * Ds * Ds, s->special, Ds, L, dir, st))) return rc;
   }
-  return do_env_advance(s, site, dir, st);
+  return do_env_advance(s, lay, site, dir, st);
 }
 
 static int do_step(const trmps_sweep* s, const trmps_layout& lay, int site, int dir, const trmps_opt* opt, cudaStream_t st) {
   return opt->single_site ? do_site_step(s, lay, site, dir, opt, st) : do_bond_step(s, lay, site, dir, opt, st);
 }
 
-static int do_init_env(const trmps_sweep* s, int loc, cudaStream_t st) {
+static int do_init_env(const trmps_sweep* s, const trmps_layout& lay, int loc, cudaStream_t st) {
   ProfScope ps(PROF_ENV, st);
   const int Ds = s->Ds, N = s->N;
   const int64_t stride = s->B * (int64_t)Ds;
   const size_t slot = (size_t)2 * Ds * Ds;
   int rc;
   if ((rc = launch_fill_boundary(s->envL, s->B, Ds, s->L, 0, st))) return rc;
+  if ((rc = launch_fill_boundary(s->envR + stride * (N - 1), s->B, Ds, s->L, 1, st))) return rc;
+  if (env_on_tensor_cores(s)) {
+    // one fused chain per side: the state stays on chip, every site's environment is written to its cache slot on the way
+    float* img = s->work + lay.env_img;
+    if (loc > 0 && (rc = launch_chain_tc(s->feat, s->feature_map, s->B, Ds, s->L, s->nodes, 0, +1, loc, 0, img, s->envL + stride * loc, st,
+                                         nullptr, s->envL + stride, stride)))
+      return rc;
+    // down to envR[loc]: the two-site sweep needs envR[loc+1], the single-site one (singlesiteOptimizer.py:38-47) envR[loc]
+    if (N - 1 - loc > 0 && (rc = launch_chain_tc(s->feat, s->feature_map, s->B, Ds, s->L, s->nodes, N - 1, -1, N - 1 - loc, 1, img,
+                                                 s->envR + stride * loc, st, nullptr, s->envR + stride * (N - 2), -stride)))
+      return rc;
+    return TRMPS_OK;
+  }
   for (int c = 0; c < loc; ++c) {
     rc = launch_env_step(s->feat + feat_site_offset(s->feature_map, s->B, c), s->feature_map, s->B, Ds, +1, s->envL + stride * c,
                          s->nodes + slot * c, s->dims + c, s->envL + stride * (c + 1), st);
     if (rc) return rc;
   }
-  if ((rc = launch_fill_boundary(s->envR + stride * (N - 1), s->B, Ds, s->L, 1, st))) return rc;
-  // down to envR[loc]: the two-site sweep needs envR[loc+1], the single-site one (singlesiteOptimizer.py:38-47) envR[loc]
   for (int c = N - 1; c > loc; --c) {
     rc = launch_env_step(s->feat + feat_site_offset(s->feature_map, s->B, c), s->feature_map, s->B, Ds, -1, s->envR + stride * c,
                          s->nodes + slot * c, s->dims + c + 1, s->envR + stride * (c - 1), st);
@@ -465,6 +483,7 @@ extern "C" int trmps_set_option(int32_t option, int32_t value) {
   if (option == 1 && (value == 0 || value == 1 || value == 2)) { g_fwd_impl = value; return TRMPS_OK; }
   if (option == 2 && (value == 0 || value == 1 || value == 2)) { g_chain_impl = value; return TRMPS_OK; }
   if (option == 3 && value >= 0 && value <= 3) { set_flat_variant(value); return TRMPS_OK; }
+  if (option == 4 && (value == 0 || value == 1)) { g_env_impl = value; return TRMPS_OK; }
   set_error("trmps_set_option: unknown option %d / value %d", option, value);
   return TRMPS_E_ARG;
 }
@@ -547,7 +566,8 @@ extern "C" int trmps_sweep_init_env(const trmps_sweep* s, int32_t loc, void* str
     set_error("trmps_sweep_init_env: loc=%d outside 0..%d", loc, s->N - 1);
     return TRMPS_E_ARG;
   }
-  return do_init_env(s, loc, (cudaStream_t)stream);
+  GET_LAYOUT(s, "trmps_sweep_init_env");
+  return do_init_env(s, lay, loc, (cudaStream_t)stream);
 }
 
 extern "C" int trmps_bond_step(const trmps_sweep* s, int32_t site, int32_t dir, const trmps_opt* opt, void* stream) {

@@ -34,7 +34,7 @@ class Opt(C.Structure):
 class Layout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
                 ("bondM", "gradM", "deltaM", "hessM", "gpart", "f0", "fd", "fpart", "resid", "sres", "hres",
-                 "phi2", "Ut", "sv", "red", "scal", "bimg", "split_ws", "total")] + \
+                 "phi2", "Ut", "sv", "red", "scal", "bimg", "split_ws", "env_img", "total")] + \
                [(n, C.c_int32) for n in ("gsplit", "nsplit", "red_rows", "svd_block", "gsplit_tc", "reserved0")]
 
 
@@ -147,6 +147,9 @@ def profile_end():
 OPT_GRAD_IMPL, GRAD_TCGEN05, GRAD_SIMT, GRAD_TCGEN05_F16 = 0, 0, 1, 2      # 0: 3xTF32 on tcgen05 (default), 2: fp16 hi/lo on tcgen05
 OPT_FWD_IMPL, FWD_TCGEN05, FWD_SIMT, FWD_TCGEN05_TF32 = 1, 0, 1, 2      # 0: fp16 hi/lo on tcgen05 (default), 2: 3xTF32 on tcgen05
 OPT_CHAIN_IMPL, CHAIN_TCGEN05, CHAIN_SIMT, CHAIN_TCGEN05_ALWAYS = 2, 0, 1, 2     # 0 falls back to 1 for chains whose rounding-bias estimate exceeds 9e-5
+
+
+OPT_ENV_IMPL, ENV_TCGEN05, ENV_SIMT = 4, 0, 1       # environments of the sweep: tensor-core chain (while its rounding-bias estimate allows) / FP32 SIMT steps
 
 
 def set_option(option, value):

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_the_header_layout():
     import ctypes as C
     assert C.sizeof(nat.Opt) == 48
-    assert C.sizeof(nat.Layout) == 19 * 8 + 6 * 4
+    assert C.sizeof(nat.Layout) == 20 * 8 + 6 * 4
     assert C.sizeof(nat.Sweep) == 4 * 4 + 2 * 8 + 2 * 4 + 10 * 8 + 8
     assert C.sizeof(nat.PredictDesc) == 4 * 4 + 8 + 4 * 4 + 6 * 8
 
@@ -64,7 +64,7 @@ def test_layout_arithmetic():
     assert lay.f0 - lay.gpart == max(lay.gsplit, lay.gsplit_tc) * R * Cc
     assert lay.gsplit == 7 and lay.gsplit_tc == 14 and lay.svd_block == 8 and 1 <= lay.nsplit <= 8
     assert lay.total - lay.bimg >= 30 * 8 * 2 * 16 * 160      # hi/lo bond images of the tensor-core forward
-    assert lay.total * 4 < 200e6
+    assert lay.total * 4 < 240e6
     for off in ("bondM", "gradM", "deltaM", "hessM", "gpart", "f0", "fd", "fpart", "resid", "sres", "hres", "phi2", "Ut", "sv", "red", "scal", "bimg", "split_ws"):
         assert getattr(lay, off) % 4 == 0
     with pytest.raises(RuntimeError):
