@@ -689,6 +689,279 @@ __global__ void __launch_bounds__(JT) split_jacobi_kernel(JacArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ 3b. Jacobi, Gram form
+// Same tournament, different work split inside a CTA (the row-pair-per-warp kernel above is bound by instruction issue:
+// every rotation costs ~140 warp instructions, a third of them the angle arithmetic repeated on all 32 lanes).  Here
+//   * the 32 x 32 Gram matrix G of the CTA's rows is formed once per round (shared-memory tiles, fixed summation order);
+//   * a CHAIN group of 8 warps runs the round's steps on G alone: 16 lanes compute the 16 angles of a step, then every
+//     thread applies the step's two rotations to one 2 x 2 block of G (G <- J^T G J).  These are exactly the rotations
+//     Hestenes' method would apply to the rows: an angle only needs three inner products;
+//   * an APPLY group of 4 warps holds the rows in registers (one or two columns per thread, all 32 rows) and replays the
+//     recorded rotations as soon as a step's angles are published (one mbarrier per step): the 4 FMAs per element are
+//     the only work done on the long rows, with compile-time register indices and no shared-memory traffic.
+// Selected with trmps_opt.split_impl = 3.  Measured at 240 x 240 (tools/split_time.py): the same sweeps, 289k cycles per
+// sweep against 303k of the kernel above -- the chain takes 650 cycles per step (two named barriers, and it shares the
+// issue slots with the apply group), the Gram matrix 3.9k and the wait for the apply group + hand-over 4.3k cycles per
+// round -- so it is not the default; it stays as the parity-tested alternative and as the starting point for a version
+// that carries the diagonal Gram blocks with the rows.
+constexpr int G2_APPLY = 128, G2_CHAIN = 256, G2_T = G2_APPLY + G2_CHAIN;
+constexpr int G2_GLD = 33, G2_STEPS_ALL = 2 * JB - 1, G2_STEPS_X = JB, G2_TILES = 36, G2_KS = 8;
+
+__device__ __forceinline__ void g2_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void g2_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void g2_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity), "r"(100000u) : "memory");
+}
+
+// replay of one step on the register-resident columns: pairs known at compile time (ALL: round-robin over the 32 rows,
+// else cross pairs i <-> JB + (i + S) % JB)
+template <int NC, bool ALL, int S>
+__device__ __forceinline__ void g2_apply_step(float (&x)[2 * JB][NC], const float2* rec_s) {
+#pragma unroll
+  for (int k = 0; k < JB; ++k) {
+    constexpr int dummy = 0; (void)dummy;
+    const int p = ALL ? rr_first(2 * JB, S, k) : k;
+    const int q = ALL ? rr_second(2 * JB, S, k) : JB + (k + S) % JB;
+    const float2 r = rec_s[k];                  // (sn, tau)
+    if (r.x != 0.f) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float u = x[p][c], w = x[q][c];
+        x[p][c] = fmaf(-r.x, fmaf(r.y, u, w), u);
+        x[q][c] = fmaf(r.x, fmaf(-r.y, w, u), w);
+      }
+    }
+  }
+}
+template <int NC, bool ALL, int S, int NS>
+struct G2ApplyLoop {
+  static __device__ __forceinline__ void run(float (&x)[2 * JB][NC], const float2 (*rec)[JB], uint64_t* bars, uint32_t& phase) {
+    g2_mbar_wait(&bars[S], (phase >> S) & 1u);
+    phase ^= 1u << S;
+    g2_apply_step<NC, ALL, S>(x, rec[S]);
+    G2ApplyLoop<NC, ALL, S + 1, NS>::run(x, rec, bars, phase);
+  }
+};
+template <int NC, bool ALL, int NS>
+struct G2ApplyLoop<NC, ALL, NS, NS> {
+  static __device__ __forceinline__ void run(float (&)[2 * JB][NC], const float2 (*)[JB], uint64_t*, uint32_t&) {}
+};
+
+template <int NC>
+__global__ void __launch_bounds__(G2_T) split_jacobi_gram_kernel(JacArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) float jsm[];                 // [2 buffers][2 slots][JB][JLD] rows, then the Gram partials
+  float* gpart = jsm + 2 * 2 * JB * JLD;                       // [G2_KS][G2_TILES * 16]
+  __shared__ float G[2][2 * JB][G2_GLD];
+  __shared__ float2 rec[G2_STEPS_ALL][JB];                     // (sn, tau) of every rotation of the round
+  __shared__ float2 coef[JB];                                  // (cos, sin) of the current step's rotations
+  __shared__ unsigned char tp[G2_STEPS_ALL + G2_STEPS_X][JB], tq[G2_STEPS_ALL + G2_STEPS_X][JB];
+  __shared__ unsigned char tile_i[G2_TILES], tile_j[G2_TILES];
+  __shared__ __align__(8) uint64_t step_bar[G2_STEPS_ALL];
+  __shared__ float wmax[2][JCL_MAX];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_apply = tid < G2_APPLY;
+  const int ct = tid - G2_APPLY;                               // chain thread index
+  const int crank = (int)cluster.block_rank();
+  const int n = 2 * *a.d_near, R = a.R;
+  const int nb = (n + JB - 1) / JB;
+  int nbe = nb + (nb & 1);
+  if (nbe < 2) nbe = 2;
+  if (nbe > 2 * a.csize) nbe = 2 * a.csize;
+  const int h = nbe / 2, rounds = nbe - 1;
+  const bool active = crank < h;
+  auto buf = [&](int b, int slot, int r) -> float* { return jsm + ((size_t)((b * 2 + slot) * JB + r)) * JLD; };
+  for (int e = tid; e < (G2_STEPS_ALL + G2_STEPS_X) * JB; e += G2_T) {
+    const int st = e / JB, j = e % JB;
+    if (st < G2_STEPS_ALL) { tp[st][j] = (unsigned char)rr_first(2 * JB, st, j); tq[st][j] = (unsigned char)rr_second(2 * JB, st, j); }
+    else { tp[st][j] = (unsigned char)j; tq[st][j] = (unsigned char)(JB + (j + st - G2_STEPS_ALL) % JB); }
+  }
+  if (tid < G2_TILES) {
+    int ti = 0, rem = tid;
+    while (rem >= 8 - ti) { rem -= 8 - ti; ++ti; }             // tiles (ti, tj), ti <= tj < 8
+    tile_i[tid] = (unsigned char)ti; tile_j[tid] = (unsigned char)(ti + rem);
+  }
+  if (tid < G2_STEPS_ALL) g2_mbar_init(&step_bar[tid], 1);
+  if (tid < 2 * JCL_MAX) (&wmax[0][0])[tid] = 0.f;
+  // ---- load: position p holds block p; CTA j has positions j (slot 0) and nbe-1-j (slot 1)
+  for (int e = tid; e < 2 * JB * (JLD / 4); e += G2_T) {
+    const int c4 = e % (JLD / 4), r = (e / (JLD / 4)) % JB, slot = e / (JB * (JLD / 4));
+    const int blk = slot == 0 ? crank : nbe - 1 - crank;
+    const int rank = blk * JB + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active && rank < n && c4 * 4 < n) v = __ldg(reinterpret_cast<const float4*>(a.Rf + (size_t)a.rowmap[rank] * R) + c4);   // columns >= n of Rf are zero
+    *reinterpret_cast<float4*>(buf(0, slot, r) + c4 * 4) = v;
+    *reinterpret_cast<float4*>(buf(1, slot, r) + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  cluster_arrive_release();
+  cluster_wait_acquire();
+  int dcta0, dslot0, dcta1, dslot1;
+  if (crank == 0) { dcta0 = 0; dslot0 = 0; } else if (crank + 1 < h) { dcta0 = crank + 1; dslot0 = 0; } else { dcta0 = h - 1; dslot0 = 1; }
+  if (crank == 0) { dcta1 = h > 1 ? 1 : 0; dslot1 = h > 1 ? 0 : 1; } else { dcta1 = crank - 1; dslot1 = 1; }
+  int cur = 0, sweeps_used = 0;
+  uint32_t phase = 0;                                          // parity of every step barrier (one bit per step)
+  const bool timer = a.dbg != nullptr && crank == 0 && warp == G2_APPLY / 32;      // first chain warp of CTA 0
+  long long tacc[4] = {0, 0, 0, 0}, tprev = timer ? clock64() : 0;
+  auto tick = [&](int k) { if (timer) { const long long now = clock64(); tacc[k] += now - tprev; tprev = now; } };
+  for (int sweep = 0; sweep < a.max_sweeps; ++sweep) {
+    float worst = 0.f;
+    for (int r = 0; r < rounds; ++r) {
+      const bool all = r == 0;                                 // first round of a sweep: every pair of the 32 rows
+      const int nsteps = all ? G2_STEPS_ALL : G2_STEPS_X;
+      if (active) {
+        float* base = jsm + (size_t)cur * 2 * JB * JLD;
+        // ---- Gram matrix: 4 x 4 register tiles (rows ti + 8 r, tj + 8 c: conflict-free float4 reads) over 8 column slices
+        if (tid < G2_TILES * G2_KS) {
+          const int tl = tid % G2_TILES, ks = tid / G2_TILES;
+          const int ti = tile_i[tl], tj = tile_j[tl];
+          float acc[4][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+          const float* pa = base + (size_t)ti * JLD + ks * 32;
+          const float* pb = base + (size_t)tj * JLD + ks * 32;
+#pragma unroll 2
+          for (int k4 = 0; k4 < 8; ++k4) {
+            float4 av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              av[i] = *reinterpret_cast<const float4*>(pa + (size_t)(8 * i) * JLD + 4 * k4);
+              bv[i] = *reinterpret_cast<const float4*>(pb + (size_t)(8 * i) * JLD + 4 * k4);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j] = dot4(av[i], bv[j], acc[i][j]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gpart[(size_t)ks * (G2_TILES * 16) + tl * 16 + i * 4 + j] = acc[i][j];
+        }
+        __syncthreads();
+        for (int e = tid; e < G2_TILES * 16; e += G2_T) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < G2_KS; ++ks) sacc += gpart[(size_t)ks * (G2_TILES * 16) + e];
+          const int tl = e >> 4, i = (e >> 2) & 3, j = e & 3;
+          const int ra = tile_i[tl] + 8 * i, rb = tile_j[tl] + 8 * j;
+          G[0][ra][rb] = sacc;
+          G[0][rb][ra] = sacc;
+        }
+        __syncthreads();
+        tick(0);
+        if (is_apply) {
+          // ---- the rows, column-wise in registers
+          float x[2 * JB][NC];
+#pragma unroll
+          for (int rr = 0; rr < 2 * JB; ++rr)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) x[rr][c] = base[(size_t)rr * JLD + tid + G2_APPLY * c];
+          if (all) G2ApplyLoop<NC, true, 0, G2_STEPS_ALL>::run(x, rec, step_bar, phase);
+          else G2ApplyLoop<NC, false, 0, G2_STEPS_X>::run(x, rec, step_bar, phase);
+          // every row goes where it is needed next (another CTA's shared memory)
+          float *dst0, *dst1;
+          if (rounds > 1) { dst0 = cluster.map_shared_rank(buf(cur ^ 1, dslot0, 0), dcta0); dst1 = cluster.map_shared_rank(buf(cur ^ 1, dslot1, 0), dcta1); }
+          else { dst0 = base; dst1 = base + (size_t)JB * JLD; }
+#pragma unroll
+          for (int rr = 0; rr < 2 * JB; ++rr)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) ((rr < JB ? dst0 : dst1) + (size_t)(rr % JB) * JLD)[tid + G2_APPLY * c] = x[rr][c];
+        } else {
+          // ---- the chain of the round's steps on the Gram matrix
+          const int iA = ct >> 4, iB = ct & 15;
+          int gc = 0;
+          for (int s = 0; s < nsteps; ++s) {
+            const int st = all ? s : G2_STEPS_ALL + s;
+            if (ct < JB) {
+              const int p = tp[st][ct], q = tq[st][ct];
+              const JRot rt = jacobi_angle(G[gc][p][p], G[gc][q][q], G[gc][p][q], a.tol);
+              coef[ct] = make_float2(rt.cs, rt.sn);
+              rec[s][ct] = make_float2(rt.sn, rt.tau);
+              worst = fmaxf(worst, rt.relg);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(G2_CHAIN) : "memory");
+            if (ct == 0) g2_mbar_arrive(&step_bar[s]);          // the apply group may replay step s
+            {
+              const int pA = tp[st][iA], qA = tq[st][iA], pB = tp[st][iB], qB = tq[st][iB];
+              const float2 ca = coef[iA], cb = coef[iB];
+              const float g00 = G[gc][pA][pB], g01 = G[gc][pA][qB], g10 = G[gc][qA][pB], g11 = G[gc][qA][qB];
+              // rows: x_p' = c x_p - s x_q, x_q' = s x_p + c x_q; then the same on the columns
+              const float r00 = ca.x * g00 - ca.y * g10, r01 = ca.x * g01 - ca.y * g11;
+              const float r10 = ca.y * g00 + ca.x * g10, r11 = ca.y * g01 + ca.x * g11;
+              G[gc ^ 1][pA][pB] = cb.x * r00 - cb.y * r01;
+              G[gc ^ 1][pA][qB] = cb.y * r00 + cb.x * r01;
+              G[gc ^ 1][qA][pB] = cb.x * r10 - cb.y * r11;
+              G[gc ^ 1][qA][qB] = cb.y * r10 + cb.x * r11;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(G2_CHAIN) : "memory");
+            gc ^= 1;
+          }
+          tick(1);
+          // the chain threads keep the barrier parities in step with the apply group
+          phase ^= all ? ((1u << G2_STEPS_ALL) - 1u) : ((1u << G2_STEPS_X) - 1u);
+        }
+      }
+      if (r == rounds - 1) {
+        // sweep maximum of |cos| over the rotated pairs (held by the 16 angle lanes) -> every CTA
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+        if (tid == G2_APPLY) {
+          for (int k = 0; k < a.csize; ++k) *cluster.map_shared_rank(&wmax[sweep & 1][crank], k) = active ? worst : 0.f;
+        }
+      }
+      cluster_arrive_release();
+      cluster_wait_acquire();
+      tick(2);
+      if (rounds > 1) cur ^= 1;
+    }
+    sweeps_used = sweep + 1;
+    float wall = 0.f;
+    for (int k = 0; k < a.csize; ++k) wall = fmaxf(wall, wmax[sweep & 1][k]);
+    if (wall < a.stop) break;
+  }
+  if (timer && lane == 0) for (int k = 0; k < 3; ++k) a.dbg[k] = (float)tacc[k];
+  // ---- normalised rows (= eigenvectors of G) and their norms, by slot index
+  if (active) {
+    for (int rr = warp; rr < 2 * JB; rr += G2_T / 32) {
+      const float* px = buf(cur, rr / JB, rr % JB) + lane * 4;
+      float4 x0 = *reinterpret_cast<const float4*>(px), x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (NC == 2) x1 = *reinterpret_cast<const float4*>(px + 128);
+      float al = dot4(x0, x0, 0.f);
+      if (NC == 2) al = dot4(x1, x1, al);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) al += __shfl_xor_sync(0xffffffffu, al, o);
+      const float nr = sqrtf(al);
+      const float inv = nr > 1e-30f ? 1.f / nr : 0.f;           // utils.check_nan: a direction that does not exist is zero
+      const int slot_row = crank * 2 * JB + rr;
+      float* out = a.X + (size_t)slot_row * R;
+      x0.x *= inv; x0.y *= inv; x0.z *= inv; x0.w *= inv;
+      x1.x *= inv; x1.y *= inv; x1.z *= inv; x1.w *= inv;
+      if (lane * 4 < R) *reinterpret_cast<float4*>(out + lane * 4) = x0;
+      if (128 + lane * 4 < R) *reinterpret_cast<float4*>(out + 128 + lane * 4) = x1;
+      if (lane == 0) a.sig[slot_row] = nr;
+    }
+  }
+  if (crank == 0 && tid == 0) {
+    a.iscal[TRMPS_I_SVD_SWEEPS] = sweeps_used;
+    a.iscal[TRMPS_I_N_SWEEPS] += sweeps_used;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ 4. ranking, m
 struct RankArgs {
   float* sig; const float* scale; int nslots; int R; const int32_t* d_near; const int32_t* d_far; int ncol_blocks;
@@ -846,31 +1119,39 @@ int split_factor(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& 
   JacArgs ja;
   ja.Rf = w.Rf; ja.R = R; ja.rowmap = w.rowmap; ja.d_near = g.d_near; ja.X = w.X; ja.sig = w.sig; ja.iscal = s->iwork;
   ja.tol = 5.9604645e-8f * sqrtf((float)R);
-  ja.stop = 3e-4f;
+  ja.stop = 1e-3f;              // quadratic convergence: a sweep whose largest |cos| was below 1e-3 leaves O(1e-6) behind
   ja.max_sweeps = opt->max_svd_sweeps > 0 ? (opt->max_svd_sweeps < 40 ? opt->max_svd_sweeps : 40) : 40;
   const int pairs = ((R + JB - 1) / JB + 1) / 2;
   ja.csize = pairs <= 1 ? 1 : pairs <= 2 ? 2 : pairs <= 4 ? 4 : 8;
   ja.dbg = s->work + lay.red;
   {
-    const size_t smem = (size_t)2 * 2 * JB * JLD * sizeof(float);
-    const bool wide = R > 128;
+    const bool wide = R > 128, gram = opt->split_impl == 3;
+    const size_t smem = (size_t)2 * 2 * JB * JLD * sizeof(float) + (gram ? (size_t)G2_KS * G2_TILES * 16 * sizeof(float) : 0);
     static bool attr_done = false;
     if (!attr_done) {
-      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int rows_b = (int)((size_t)2 * 2 * JB * JLD * sizeof(float)), gram_b = rows_b + (int)((size_t)G2_KS * G2_TILES * 16 * sizeof(float));
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_b));
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_b));
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_gram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_b));
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_gram_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_b));
       attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ja.csize);
-    cfg.blockDim = dim3(JT);
+    cfg.blockDim = dim3(gram ? G2_T : JT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = ja.csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (wide) TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_kernel<true>, ja));
-    else TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_kernel<false>, ja));
+    if (gram) {
+      if (wide) TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_gram_kernel<2>, ja));
+      else TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_gram_kernel<1>, ja));
+    } else {
+      if (wide) TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_kernel<true>, ja));
+      else TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_kernel<false>, ja));
+    }
     count_launch();
   }
   // 4. ranking

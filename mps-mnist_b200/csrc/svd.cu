@@ -774,7 +774,7 @@ static int launch_jacobi(SvdArgs& a, int ncta, cudaStream_t st) {
 int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, cudaStream_t st,
               float* special_out, bool single) {
   const int Ds = s->Ds, L = s->L, R = 2 * Ds, Cc = 2 * L * Ds;
-  if (opt->split_impl == 0 && split_factor_supported(R)) return split_factor(s, lay, g, opt, st, special_out, single);
+  if (opt->split_impl != 1 && split_factor_supported(R)) return split_factor(s, lay, g, opt, st, special_out, single);
   const int blk = lay.svd_block;
   if (blk == 0) {
     set_error("svd: bond stride Ds=%d (R=%d, Cc=%d) is outside the supported range (Cc <= 5120, R <= 512)", Ds, R, Cc);

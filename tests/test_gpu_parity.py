@@ -174,9 +174,10 @@ def test_merge_forward_gradient(direction, D):
 
 
 # --------------------------------------------------------------------------------------------- split (SVD)
+@pytest.mark.parametrize("impl", [0, 1, 3])      # trmps_opt.split_impl: factor + Jacobi in one cluster (default), Jacobi on the bond rows, Gram-form kernel
 @pytest.mark.parametrize("direction", [+1, -1])
 @pytest.mark.parametrize("D,max_size", [(None, 24), (24, 24), (40, 32)])
-def test_split_matches_lapack(direction, D, max_size):
+def test_split_matches_lapack(direction, D, max_size, impl):
     N, B, L, loc = 6, 64, 10, 3
     pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=31, full_bond=D, loc=loc)
     st = make_state(N, B, L, max(max_size, D or 0), nodes, loc, phi, lab)
@@ -185,7 +186,7 @@ def test_split_matches_lapack(direction, D, max_size):
     p = o.SweepParams(max_size=max_size, min_singular_value=1e-4)
     tr = o.Trace(); tr.append({})
     a_j, a_j1 = o.bond_decomposition(bond, p, tr)
-    opt = dev.make_opt(lr=0.1, max_size=max_size, min_singular_value=1e-4)
+    opt = dev.make_opt(lr=0.1, max_size=max_size, min_singular_value=1e-4, split_impl=impl)
     st.bond_split(loc, direction, opt)
     torch.cuda.synchronize()
     iw = st.iwork.cpu().numpy()
