@@ -107,6 +107,8 @@ typedef struct {
   int32_t split_impl;         /* 0: Jacobi on the Cholesky factor of the bond's Gram matrix inside one thread-block cluster
                                  (split_factor.cu; R = 2*Ds <= 256), falling back to 1 for larger bonds;
                                  1: Jacobi on the rows of the bond matrix itself (svd.cu);
+                                 2: as 0 with blocks of 16 rows (clusters of at most 8 CTAs: what 0 falls back to when the device
+                                 cannot schedule a 16-CTA cluster);
                                  3: as 0 with the Gram-form Jacobi kernel (rotation chain on the CTA's 32 x 32 Gram matrix by
                                  one warp group, rows replayed from registers by another) */
   int32_t reserved;

@@ -411,11 +411,9 @@ __global__ void __launch_bounds__(CT) split_chol_kernel(CholArgs a) {
 
 // ------------------------------------------------------------------------------------------------ 3. Jacobi
 constexpr int JB = 16;                 // rows per block
-constexpr int JWARPS = 8, JT = 32 * JWARPS;
 constexpr int JLD = SP_NMAX + 4;       // row stride in shared memory (floats): 16-byte rows, conflict-free float4 access;
                                        // float SP_NMAX of a row carries its squared norm through the rotations
-constexpr int JCL_MAX = 8;             // CTAs per cluster = block pairs per round
-constexpr int JPH_CROSS = 8, JPH_ALL = 16;
+constexpr int JCL_MAX = 16;            // CTAs per cluster = block pairs per round (16: non-portable cluster size)
 
 struct JacArgs {
   const float* Rf; int R; const int32_t* rowmap; const int32_t* d_near; float* X; float* sig; int32_t* iscal;
@@ -544,8 +542,12 @@ __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.c
 // rotation made shared-memory bandwidth the limit: 64 KB per step).  Cross-block pairs: 8 phases.  Pairs inside a block
 // (once per sweep): the same scheme applied to halves, quarters, eighths of a block (4 + 2 + 1 phases) and a last phase
 // for the pairs inside the groups of two: 31 steps in all, the minimum for 32 rows.
-template <bool WIDE>
-__global__ void __launch_bounds__(JT) split_jacobi_kernel(JacArgs a) {
+// BR = rows per block: 16 (8 warps per CTA, clusters of up to 8) or 8 (4 warps per CTA -- one per scheduler, so a phase runs
+// at a single warp's latency instead of two warps sharing the issue slots -- and clusters of up to 16 CTAs, a
+// non-portable size the host enables when the device can schedule it).
+template <bool WIDE, int BR>
+__global__ void __launch_bounds__(16 * BR) split_jacobi_kernel(JacArgs a) {
+  constexpr int JB = BR, JWARPS = BR / 2, JT = 16 * BR, JPH_CROSS = BR / 2, JPH_ALL = BR;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) float jsm[];                 // [2 buffers][2 slots][JB][JLD]
   __shared__ float wmax[2][JCL_MAX];
@@ -563,13 +565,28 @@ __global__ void __launch_bounds__(JT) split_jacobi_kernel(JacArgs a) {
   const bool active = crank < h;
   auto buf = [&](int b, int slot, int r) -> float* { return jsm + ((size_t)((b * 2 + slot) * JB + r)) * JLD; };
   if (tid < JPH_ALL * JWARPS) {
+    // phase table: cross-block pairs first (x rows from block A, y rows from block B), then the pairs inside the blocks:
+    // the same 2 x 2 scheme on groups of BR, BR/2, .. 4 rows (x from the first half of a group, y from the second), and
+    // a last phase for the pairs inside the groups of two
     const int ph = tid / JWARPS, w = tid % JWARPS;
-    int xa, xb, ya, yb, fl;
-    if (ph < 8) { const int t = ph, y = 16 + 2 * ((w + t) % 8); xa = 2 * w; xb = xa + 1; ya = y; yb = y + 1; fl = (t == 0 ? 1 : 0) | (t == 7 ? 2 : 0); }
-    else if (ph < 12) { const int t = ph - 8, g = 16 * (w / 4), q = w % 4, y = g + 8 + 2 * ((q + t) % 4); xa = g + 2 * q; xb = xa + 1; ya = y; yb = y + 1; fl = (t == 0 ? 1 : 0) | (t == 3 ? 2 : 0); }
-    else if (ph < 14) { const int t = ph - 12, g = 8 * (w / 2), q = w % 2, y = g + 4 + 2 * ((q + t) % 2); xa = g + 2 * q; xb = xa + 1; ya = y; yb = y + 1; fl = (t == 0 ? 1 : 0) | (t == 1 ? 2 : 0); }
-    else if (ph == 14) { const int g = 4 * w; xa = g; xb = g + 1; ya = g + 2; yb = g + 3; fl = 3; }
-    else { const int g = 4 * w; xa = g; ya = g + 1; xb = g + 2; yb = g + 3; fl = 7; }
+    int xa = 0, xb = 0, ya = 0, yb = 0, fl = 0;
+    if (ph < JPH_CROSS) {
+      const int t = ph, y = JB + 2 * ((w + t) % JWARPS);
+      xa = 2 * w; xb = xa + 1; ya = y; yb = y + 1; fl = (t == 0 ? 1 : 0) | (t == JPH_CROSS - 1 ? 2 : 0);
+    } else {
+      int rest = ph - JPH_CROSS, S = JB;
+      bool done = false;
+      while (S >= 4 && !done) {
+        const int np = S / 4;                    // phases of this level = warps per group
+        if (rest < np) {
+          const int t = rest, g = S * (w / np), q = w % np, y = g + S / 2 + 2 * ((q + t) % np);
+          xa = g + 2 * q; xb = xa + 1; ya = y; yb = y + 1; fl = (t == 0 ? 1 : 0) | (t == np - 1 ? 2 : 0);
+          done = true;
+        }
+        rest -= np; S /= 2;
+      }
+      if (!done) { const int g = 4 * w; xa = g; ya = g + 1; xb = g + 2; yb = g + 3; fl = 7; }
+    }
     tab_rows[ph][w] = make_uchar4((unsigned char)xa, (unsigned char)xb, (unsigned char)ya, (unsigned char)yb);
     tab_flags[ph][w] = (unsigned char)fl;
   }
@@ -964,7 +981,7 @@ __global__ void __launch_bounds__(G2_T) split_jacobi_gram_kernel(JacArgs a) {
 
 // ------------------------------------------------------------------------------------------------ 4. ranking, m
 struct RankArgs {
-  float* sig; const float* scale; int nslots; int R; const int32_t* d_near; const int32_t* d_far; int ncol_blocks;
+  float* sig; const float* scale; int nslots; int block_rows; int R; const int32_t* d_near; const int32_t* d_far; int ncol_blocks;
   float* sv; int32_t* order; int32_t* iscal; int32_t* dim_out; float min_sv; int max_size, min_size;
 };
 
@@ -973,10 +990,10 @@ __global__ void __launch_bounds__(SP_NMAX) split_rank_kernel(RankArgs a) {
   __shared__ int s_count;
   const int tid = threadIdx.x;
   const int n = 2 * *a.d_near;
-  const int nb = (n + JB - 1) / JB;
+  const int nb = (n + a.block_rows - 1) / a.block_rows;
   int nbe = nb + (nb & 1);
   if (nbe < 2) nbe = 2;
-  const int nslots = min(a.nslots, nbe * JB);
+  const int nslots = min(a.nslots, nbe * a.block_rows);
   if (tid == 0) s_count = 0;
   sg[tid] = tid < nslots ? a.sig[tid] * a.scale[0] : -1.f;
   __syncthreads();
@@ -1121,24 +1138,47 @@ int split_factor(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& 
   ja.tol = 5.9604645e-8f * sqrtf((float)R);
   ja.stop = 1e-3f;              // quadratic convergence: a sweep whose largest |cos| was below 1e-3 leaves O(1e-6) behind
   ja.max_sweeps = opt->max_svd_sweeps > 0 ? (opt->max_svd_sweeps < 40 ? opt->max_svd_sweeps : 40) : 40;
-  const int pairs = ((R + JB - 1) / JB + 1) / 2;
-  ja.csize = pairs <= 1 ? 1 : pairs <= 2 ? 2 : pairs <= 4 ? 4 : 8;
+  // rows per block: 8 when the cluster this needs (up to 16 CTAs for R = 256: a non-portable size) can be scheduled, else 16
+  const bool gram = opt->split_impl == 3, wide = R > 128;
+  static int big_cluster_ok = -1;                 // can a 16-CTA cluster of the 8-row kernel run on this device?
+  if (big_cluster_ok < 0) {
+    big_cluster_ok = 0;
+    const size_t smem8 = (size_t)2 * 2 * 8 * JLD * sizeof(float);
+    if (cudaFuncSetAttribute(split_jacobi_kernel<true, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(split_jacobi_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8) == cudaSuccess) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(16); q.blockDim = dim3(128); q.dynamicSmemBytes = smem8;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 16; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, split_jacobi_kernel<true, 8>, &q) == cudaSuccess && ncl > 0) big_cluster_ok = 1;
+    }
+    (void)cudaGetLastError();
+  }
+  int br = (gram || opt->split_impl == 2) ? 16 : 8;
+  int pairs = ((R + br - 1) / br + 1) / 2;
+  if (br == 8 && pairs > 8 && !big_cluster_ok) { br = 16; pairs = ((R + br - 1) / br + 1) / 2; }
+  ja.csize = pairs <= 1 ? 1 : pairs <= 2 ? 2 : pairs <= 4 ? 4 : pairs <= 8 ? 8 : 16;
   ja.dbg = s->work + lay.red;
   {
-    const bool wide = R > 128, gram = opt->split_impl == 3;
-    const size_t smem = (size_t)2 * 2 * JB * JLD * sizeof(float) + (gram ? (size_t)G2_KS * G2_TILES * 16 * sizeof(float) : 0);
+    const size_t smem = (size_t)2 * 2 * br * JLD * sizeof(float) + (gram ? (size_t)G2_KS * G2_TILES * 16 * sizeof(float) : 0);
     static bool attr_done = false;
     if (!attr_done) {
-      const int rows_b = (int)((size_t)2 * 2 * JB * JLD * sizeof(float)), gram_b = rows_b + (int)((size_t)G2_KS * G2_TILES * 16 * sizeof(float));
-      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_b));
-      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_b));
+      const int rows16 = (int)((size_t)2 * 2 * 16 * JLD * sizeof(float)), rows8 = rows16 / 2;
+      const int gram_b = rows16 + (int)((size_t)G2_KS * G2_TILES * 16 * sizeof(float));
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows16));
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows16));
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows8));
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows8));
       TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_gram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_b));
       TRMPS_CUDA_OK(cudaFuncSetAttribute(split_jacobi_gram_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_b));
       attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ja.csize);
-    cfg.blockDim = dim3(gram ? G2_T : JT);
+    cfg.blockDim = dim3(gram ? G2_T : 16 * br);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -1148,15 +1188,18 @@ int split_factor(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& 
     if (gram) {
       if (wide) TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_gram_kernel<2>, ja));
       else TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_gram_kernel<1>, ja));
+    } else if (br == 8) {
+      if (wide) TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_kernel<true, 8>, ja));
+      else TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_kernel<false, 8>, ja));
     } else {
-      if (wide) TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_kernel<true>, ja));
-      else TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_kernel<false>, ja));
+      if (wide) TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_kernel<true, 16>, ja));
+      else TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_jacobi_kernel<false, 16>, ja));
     }
     count_launch();
   }
   // 4. ranking
   RankArgs ra;
-  ra.sig = w.sig; ra.scale = w.scale; ra.nslots = ja.csize * 2 * JB; ra.R = R; ra.d_near = g.d_near; ra.d_far = g.d_far;
+  ra.sig = w.sig; ra.scale = w.scale; ra.nslots = ja.csize * 2 * br; ra.block_rows = br; ra.R = R; ra.d_near = g.d_near; ra.d_far = g.d_far;
   ra.ncol_blocks = single ? L : 2 * L;
   ra.sv = s->work + lay.sv;
   ra.order = reinterpret_cast<int32_t*>(s->work + lay.sv + R);

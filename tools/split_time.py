@@ -40,6 +40,6 @@ for L in [int(v) for v in (sys.argv[2:] or ["10"])]:
                 dbg = st.work[st.layout.red: st.layout.red + 3].cpu().numpy(); ns = int(st.iwork.cpu()[nat.I_SVD_SWEEPS])
                 cd = st.work[st.layout.red + 8: st.layout.red + 14].cpu().numpy()
                 print("   cholesky cycles: G+D load %.0f  update %.0f  reduce %.0f  diagonal block %.0f  solve+write %.0f  norms+rank %.0f" % tuple(cd))
-                print("   jacobi CTA 0 chain warp, cycles per sweep: gram %.0f  chain %.0f  wait for apply/hand-over + cluster barrier %.0f" % tuple(dbg[:3] / ns))
+                print("   jacobi CTA 0 warp 0, cycles per sweep: rotations + hand-over %.0f  cluster barrier %.0f" % tuple(dbg[:2] / ns))
             print("impl %d %-9s L=%d D=%d bond %s: split %.3f ms (min of %s), sweeps %d, m %d, sigma rel err %.1e" %
                   (impl, kind, L, D, tuple(bm.shape), min(ts), ["%.3f" % t for t in ts], int(st.iwork.cpu()[nat.I_SVD_SWEEPS]), m, res))
