@@ -395,7 +395,7 @@ def run_ours(args, rank, local_rank, world):
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             logits = net.predict(hpix, feature_map=nat.FM_COS_SIN)
-            logits = np.asarray(logits)
+            logits = logits.cpu().numpy() if hasattr(logits, "cpu") else np.asarray(logits)      # D2H of the result
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0, torch.float64)
         if rank == 0:
