@@ -432,6 +432,47 @@ __device__ __forceinline__ void rot4(float4& x, float4& y, float sn, float tau) 
   u = x.w; w = y.w; x.w = fmaf(-sn, fmaf(tau, u, w), u); y.w = fmaf(sn, fmaf(-tau, w, u), w);
 }
 
+// ---- hand-over of the row blocks without a cluster-wide barrier: the rows are written into the next CTA's shared memory
+// with st.async, which signals the bytes on an mbarrier in THAT CTA; the receiver waits for its own bytes only (its two
+// ring neighbours), not for the slowest CTA of the cluster, and no release fence has to drain (the cluster barrier's
+// MEMBAR + wait were 19 % of the kernel's stall samples, profiles/r2f_split_and_env_kernels_ncu.txt)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, int cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f4(uint32_t raddr, const float4& v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(raddr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async_f1(uint32_t raddr, float v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(__float_as_uint(v)), "r"(rbar) : "memory");
+}
+// one bulk copy of a whole row from this CTA's shared memory into another CTA's, bytes signalled on that CTA's mbarrier
+// (per-thread st.async stores cost the receiver one mbarrier transaction per lane: 1040 per round, measured slower than the
+// cluster barrier they replaced)
+__device__ __forceinline__ void bulk_row_to_cta(uint32_t raddr, uint32_t local_addr, uint32_t bytes, uint32_t rbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(raddr), "r"(local_addr), "r"(bytes), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init_cta(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_cta(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cta(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_addr(bar)), "r"(parity), "r"(100000u) : "memory");
+}
+
 // a row of the factor spread over one warp: lane holds columns 4 lane .. 4 lane + 3 (and 128 + the same when WIDE);
 // nrm = squared norm, carried through the rotations (al' = al - t ga, be' = be + t ga, exact for the exact Jacobi angle)
 // and refreshed from the data once per sweep: it only steers the angle, so its rounding drift cannot bias the
@@ -439,15 +480,23 @@ __device__ __forceinline__ void rot4(float4& x, float4& y, float sn, float tau) 
 template <bool WIDE>
 struct JRow {
   float4 lo, hi; float nrm;
+  static constexpr int NPOS = WIDE ? SP_NMAX : 128;       // float of the row that carries the squared norm (right behind the data)
   __device__ __forceinline__ void load(const float* p, int lane) {
     lo = *reinterpret_cast<const float4*>(p + lane * 4);
     if (WIDE) hi = *reinterpret_cast<const float4*>(p + 128 + lane * 4);
-    nrm = p[SP_NMAX];
+    nrm = p[NPOS];
   }
   __device__ __forceinline__ void store(float* p, int lane) const {
     *reinterpret_cast<float4*>(p + lane * 4) = lo;
     if (WIDE) *reinterpret_cast<float4*>(p + 128 + lane * 4) = hi;
-    if (lane == 0) p[SP_NMAX] = nrm;
+    if (lane == 0) p[NPOS] = nrm;
+  }
+  // the same into another CTA's shared memory (shared::cluster address raddr), bytes signalled on its mbarrier rbar
+  static constexpr uint32_t ASYNC_BYTES = (WIDE ? 1024u : 512u) + 4u;
+  __device__ __forceinline__ void store_async(uint32_t raddr, uint32_t rbar, int lane) const {
+    st_async_f4(raddr + (uint32_t)lane * 16u, lo, rbar);
+    if (WIDE) st_async_f4(raddr + 512u + (uint32_t)lane * 16u, hi, rbar);
+    if (lane == 0) st_async_f1(raddr + (uint32_t)NPOS * 4u, nrm, rbar);
   }
 };
 
@@ -552,6 +601,7 @@ __global__ void __launch_bounds__(16 * BR) split_jacobi_kernel(JacArgs a) {
   extern __shared__ __align__(16) float jsm[];                 // [2 buffers][2 slots][JB][JLD]
   __shared__ float wmax[2][JCL_MAX];
   __shared__ float wwarp[JWARPS];
+  __shared__ __align__(8) uint64_t rx_bar[2];                  // rx_bar[b]: the two blocks of buffer b have arrived
   __shared__ uchar4 tab_rows[JPH_ALL][JWARPS];
   __shared__ unsigned char tab_flags[JPH_ALL][JWARPS];         // 1: load x rows, 2: store x rows, 4: first half only
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -601,6 +651,8 @@ __global__ void __launch_bounds__(16 * BR) split_jacobi_kernel(JacArgs a) {
     *reinterpret_cast<float4*>(buf(1, slot, r) + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (tid < 2 * JCL_MAX) (&wmax[0][0])[tid] = 0.f;
+  if (tid < 2) mbar_init_cta(&rx_bar[tid], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   cluster_arrive_release();
   cluster_wait_acquire();
@@ -609,6 +661,9 @@ __global__ void __launch_bounds__(16 * BR) split_jacobi_kernel(JacArgs a) {
   if (crank == 0) { dcta0 = 0; dslot0 = 0; } else if (crank + 1 < h) { dcta0 = crank + 1; dslot0 = 0; } else { dcta0 = h - 1; dslot0 = 1; }
   if (crank == 0) { dcta1 = h > 1 ? 1 : 0; dslot1 = h > 1 ? 0 : 1; } else { dcta1 = crank - 1; dslot1 = 1; }
   int cur = 0, sweeps_used = 0;
+  uint32_t rx_phase = 0;                                       // parity of rx_bar[b] in bit b
+  constexpr uint32_t ROW_BYTES = (JRow<WIDE>::NPOS + 4) * 4u, RX_BYTES = 2u * JB * ROW_BYTES;      // data + the float4 holding the carried norm
+  constexpr uint32_t ROW_STRIDE = JLD * 4u;
   const bool timer = a.dbg != nullptr && crank == 0 && warp == 0;     // warp-uniform: a per-thread branch would make the shuffles divergence-checked
   long long tacc[2] = {0, 0}, tprev = timer ? clock64() : 0;
   auto tick = [&](int k) { if (timer) { const long long now = clock64(); tacc[k] += now - tprev; tprev = now; } };
@@ -617,11 +672,26 @@ __global__ void __launch_bounds__(16 * BR) split_jacobi_kernel(JacArgs a) {
     for (int r = 0; r < rounds; ++r) {
       if (active) {
         float* base = jsm + (size_t)cur * 2 * JB * JLD;
-        // the last phase of a round stores every row: it stores them where they are needed next (another CTA's shared memory)
-        float *dst0, *dst1;
-        if (rounds > 1) { dst0 = cluster.map_shared_rank(buf(cur ^ 1, dslot0, 0), dcta0); dst1 = cluster.map_shared_rank(buf(cur ^ 1, dslot1, 0), dcta1); }
-        else { dst0 = base; dst1 = base + (size_t)JB * JLD; }
-        auto dstrow = [&](int row) -> float* { return (row < JB ? dst0 : dst1) + (size_t)(row % JB) * JLD; };
+        // the last phase of a round stores every row: it stores them where they are needed next (another CTA's shared
+        // memory, st.async + that CTA's mbarrier); this CTA expects its own two blocks for the other buffer
+        const bool xchg = rounds > 1;
+        uint32_t rdst0 = 0, rdst1 = 0, rbar0 = 0, rbar1 = 0;
+        if (xchg) {
+          rdst0 = map_to_cta(smem_addr(buf(cur ^ 1, dslot0, 0)), dcta0); rbar0 = map_to_cta(smem_addr(&rx_bar[cur ^ 1]), dcta0);
+          rdst1 = map_to_cta(smem_addr(buf(cur ^ 1, dslot1, 0)), dcta1); rbar1 = map_to_cta(smem_addr(&rx_bar[cur ^ 1]), dcta1);
+          if (tid == 0) mbar_expect_tx_cta(&rx_bar[cur ^ 1], RX_BYTES);
+        }
+        // a row goes back into this CTA's buffer and from there, as one bulk copy, to its next owner
+        auto send = [&](const JRow<WIDE>& row_v, int row) {
+          float* loc = base + (size_t)row * JLD;
+          row_v.store(loc, lane);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (row < JB) bulk_row_to_cta(rdst0 + (uint32_t)row * ROW_STRIDE, smem_addr(loc), ROW_BYTES, rbar0);
+            else bulk_row_to_cta(rdst1 + (uint32_t)(row - JB) * ROW_STRIDE, smem_addr(loc), ROW_BYTES, rbar1);
+          }
+        };
         if (r == 0) {
           // squared norms from the data (four rows per warp)
 #pragma unroll
@@ -632,7 +702,7 @@ __global__ void __launch_bounds__(16 * BR) split_jacobi_kernel(JacArgs a) {
             if (WIDE) { const float4 x1 = *reinterpret_cast<const float4*>(p + 128 + lane * 4); al += dot4(x1, x1, 0.f); }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) al += __shfl_xor_sync(0xffffffffu, al, o);
-            if (lane == 0) p[SP_NMAX] = al;
+            if (lane == 0) p[JRow<WIDE>::NPOS] = al;
           }
           __syncthreads();
         }
@@ -644,9 +714,12 @@ __global__ void __launch_bounds__(16 * BR) split_jacobi_kernel(JacArgs a) {
           if (fl & 1) { xa.load(base + (size_t)rw.x * JLD, lane); xb.load(base + (size_t)rw.y * JLD, lane); }
           ya.load(base + (size_t)rw.z * JLD, lane); yb.load(base + (size_t)rw.w * JLD, lane);
           worst = fmaxf(worst, jacobi_quad<WIDE>(xa, xb, ya, yb, a.tol, (fl & 4) != 0));
-          if (ph == nph - 1) {
-            ya.store(dstrow(rw.z), lane); yb.store(dstrow(rw.w), lane);
-            xa.store(dstrow(rw.x), lane); xb.store(dstrow(rw.y), lane);
+          if (ph == nph - 1 && xchg) {
+            send(ya, rw.z); send(yb, rw.w); send(xa, rw.x); send(xb, rw.y);
+          } else if (ph == nph - 1) {
+            ya.store(base + (size_t)rw.z * JLD, lane); yb.store(base + (size_t)rw.w * JLD, lane);
+            xa.store(base + (size_t)rw.x * JLD, lane); xb.store(base + (size_t)rw.y * JLD, lane);
+            __syncthreads();
           } else {
             ya.store(base + (size_t)rw.z * JLD, lane); yb.store(base + (size_t)rw.w * JLD, lane);
             if (fl & 2) { xa.store(base + (size_t)rw.x * JLD, lane); xb.store(base + (size_t)rw.y * JLD, lane); }
@@ -668,10 +741,19 @@ __global__ void __launch_bounds__(16 * BR) split_jacobi_kernel(JacArgs a) {
         }
       }
       tick(0);
-      cluster_arrive_release();
-      cluster_wait_acquire();
+      if (active && rounds > 1) {
+        // my two blocks of the next round (from my ring neighbours); a sender cannot overwrite a buffer its receiver still
+        // reads: it needs that receiver's previous output first (every edge of the ring is used in both directions)
+        mbar_wait_cta(&rx_bar[cur ^ 1], (rx_phase >> (cur ^ 1)) & 1u);
+        rx_phase ^= 1u << (cur ^ 1);
+        cur ^= 1;
+      }
+      if (r == rounds - 1) {
+        // once per sweep: the convergence flags of all CTAs (and, after the last sweep, nobody leaves while a store is in flight)
+        cluster_arrive_release();
+        cluster_wait_acquire();
+      }
       tick(1);
-      if (rounds > 1) cur ^= 1;
     }
     sweeps_used = sweep + 1;
     float wall = 0.f;
