@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(CT) split_chol_kernel(CholArgs a) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int k = g + ngr * (8 * b + u);
-        r[u] = (upd && k < c0) ? __ldcg(&a.Rd[(size_t)k * R + irow]) : 0.0;
+        r[u] = (upd && k < c0) ? a.Rd[(size_t)k * R + irow] : 0.0;      // L1-cached: a row of R is final once written and is re-read by every later panel
       }
     };
     // ---- columns c0 .. c0+w-1 of G (stored in full: read as rows, unit stride), D[k][c] = Rd[k][c0 + c] and the first batch
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(CT) split_chol_kernel(CholArgs a) {
 #pragma unroll
       for (int u = 0; u < CNE; ++u) {
         const int e = tid + u * CT, k = e / CW, c = e % CW;
-        dv[u] = (e < c0 * CW && c < w) ? __ldcg(&a.Rd[(size_t)k * R + c0 + c]) : 0.0;
+        dv[u] = (e < c0 * CW && c < w) ? a.Rd[(size_t)k * R + c0 + c] : 0.0;
       }
       rd_load(0, r0);
 #pragma unroll
