@@ -175,7 +175,19 @@ __global__ void chain_exp_kernel(const float* __restrict__ nodes, int32_t* __res
   const int s = blockIdx.x;
   const float* node = nodes + (size_t)(first + s * dir) * 2 * Ds * Ds;
   float m = 0.f;
-  for (int e = threadIdx.x; e < 2 * Ds * Ds; e += blockDim.x) m = fmaxf(m, fabsf(node[e]));
+  // 2 Ds^2 floats, Ds a multiple of 4: float4 loads, eight in flight per thread (one L2 round trip instead of 28)
+  const float4* node4 = reinterpret_cast<const float4*>(node);
+  const int n4 = (2 * Ds * Ds) >> 2;
+  for (int e0 = threadIdx.x; e0 < n4; e0 += 8 * blockDim.x) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * blockDim.x;
+      v[u] = e < n4 ? __ldg(node4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) m = fmaxf(m, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;

@@ -349,13 +349,23 @@ __global__ void grad_finish_kernel(float* __restrict__ G, const float* __restric
   if (threadIdx.x == 0) red[blockIdx.x * 32] = s;
 }
 
-// dst[c] = scale * sum_r red[r][c]  for c < ncols, rows summed in order by one warp per column group
-__global__ void sum_red_kernel(const float* __restrict__ red, int nrows, int ncols, float scale, float* __restrict__ dst) {
-  int c = threadIdx.x;
-  if (c >= ncols) return;
+// dst[c] = scale * sum_r red[r][c]  for c < ncols <= 32: 32 row groups sum their rows (r = g, g + 32, ..) in order, then the groups
+// are added in order -- a fixed summation order (every rank gets the same bits) with 32 loads in flight per column
+// instead of one warp walking all rows
+__global__ void __launch_bounds__(1024) sum_red_kernel(const float* __restrict__ red, int nrows, int ncols, float scale, float* __restrict__ dst) {
+  __shared__ float part[32][33];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
   float s = 0.f;
-  for (int r = 0; r < nrows; ++r) s += red[r * 32 + c];
-  dst[c] = s * scale;
+  if (c < ncols)
+    for (int r = g; r < nrows; r += 32) s += red[r * 32 + c];
+  part[g][c] = s;
+  __syncthreads();
+  if (g == 0 && c < ncols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += part[k][c];
+    dst[c] = t * scale;
+  }
 }
 
 // =================================================================================================
@@ -600,7 +610,7 @@ int launch_armijo(const ArmijoArgs& a, cudaStream_t st) {
   return TRMPS_OK;
 }
 int launch_sum_red(const float* red, int nrows, int ncols, float scale, float* dst, cudaStream_t st) {
-  sum_red_kernel<<<1, 32, 0, st>>>(red, nrows, ncols, scale, dst);
+  sum_red_kernel<<<1, 1024, 0, st>>>(red, nrows, ncols, scale, dst);
   TRMPS_LAUNCH_OK("sum_red_kernel");
   return TRMPS_OK;
 }
