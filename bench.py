@@ -448,7 +448,7 @@ def run_ours(args, rank, local_rank, world):
         optim.bind_batch(pix_pin, lab_pin, weights=nodes)
         return optim, pix_pin, lab_pin
 
-    def timed_steps(optim, steps, warmup, profile):
+    def timed_steps(optim, steps, warmup, profile, graph=False):
         st = optim._state
         opt = optim._opt(lr)
         slots0, special0, dims0 = st.slots.clone(), st.special.clone(), st.dims.clone()
@@ -468,6 +468,16 @@ def run_ours(args, rank, local_rank, world):
 
         for _ in range(warmup):
             device_step()
+        run_step = device_step
+        if graph:
+            # the whole step (every kernel of the three half-sweeps, the NCCL all-reduces included) as ONE CUDA graph: possible
+            # because no kernel of the sweep is a cooperative launch any more and nothing on the path synchronises with the host
+            barrier()
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                device_step()
+            run_step = cg.replay
+            run_step()
         if cfg["kind"] != "l2r":
             reset()                       # the timed steps start from the initial MPS again
         barrier()
@@ -478,7 +488,7 @@ def run_ours(args, rank, local_rank, world):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(steps):
-            device_step()
+            run_step()
         ev1.record()
         barrier()
         launches = nat.launch_count() - l0
@@ -535,6 +545,19 @@ def run_ours(args, rank, local_rank, world):
     h2d = pix_pin.numel() * 4 + lab_pin.numel() * 4 + sum(w.nbytes for w in nodes)
     d2h = sum(w.nbytes for w in out_nodes) + 4
     Dp = st.Ds
+
+    # secondary number: the same steps replayed from one CUDA graph (launch-bound configurations gain; cfg3 does not)
+    graph_line = None
+    if args.graph == "on" or (args.graph == "auto" and world == 1):
+        try:
+            gms, _, _, _ = timed_steps(optim, args.steps, 1, False, graph=True)
+            graph_line = dict(value=world * B * bonds * args.steps / (gms * 1e-3), unit=UNIT, ms_per_step=gms / args.steps, steps=args.steps,
+                              note="the same timed steps replayed from ONE captured CUDA graph per step (cudaGraphLaunch instead of %d kernel "
+                                   "launches); `value` above is the plain stream-launch number the breakdown belongs to"
+                                   % (launches // max(args.steps, 1)))
+        except Exception as exc:                      # a failed capture must not cost the headline line
+            graph_line = dict(error=str(exc)[:300])
+            torch.cuda.synchronize()
 
     # secondary number at N > 1: the same step with the per-GPU batch held at the full batch (weak scaling)
     weak = None
@@ -677,6 +700,8 @@ def run_ours(args, rank, local_rank, world):
                           source=peaks["source"]))
     if weak is not None:
         out["weak_scaling"] = weak
+    if graph_line is not None:
+        out["cuda_graph"] = graph_line
     if inference is not None:
         out.update(inference=inference, inference_cfg5=inference_cfg5, roofline_datasource=datasource)
     if world == 1 and not args.no_cpu_baseline:
@@ -715,6 +740,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="skip the secondary weak-scaling measurement at N > 1")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="also time the steps replayed from a captured CUDA graph (secondary key cuda_graph); auto = on one GPU only")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="strong (default, BASELINE.json: '60k images, batch-sharded at 1/2/4/8'): the configuration's images in total, "
                          "sharded over the GPUs; weak: that many images on every GPU")
