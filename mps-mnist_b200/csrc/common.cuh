@@ -181,6 +181,9 @@ int64_t forward_tc_image_floats(int Ds, int L);
 int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_near, const float* phi_far, const float* M,
                       float* bimg, float* f_out, int64_t B, int Ds, int L, const int32_t* d_near, const int32_t* d_far,
                       cudaStream_t st);
+bool forward_site_tc_supported(int Ds, int L);
+int launch_forward_site_tc(const float* e_near, const float* e_far, const float* phi_near, const float* special, int dir, float* bimg,
+                           float* f_out, int64_t B, int Ds, int L, const int32_t* d_near, const int32_t* d_far, cudaStream_t st);
 int forward_rq(int Ds, int L);
 int svd_block_rows(int R, int Cc);
 

@@ -376,10 +376,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // one accumulator tile, my half of its columns (16-column chunks [HALF*NCH, (HALF+1)*NCH)): every column has a
-// compile-time (k_local; l, m, n)
-template <int L, int HALF>
-__device__ __forceinline__ void fh_epilogue_tile(uint32_t taddr, const float (&pp)[4], const float (&ek)[4], float (&facc)[L]) {
+// compile-time (k_local; l, m, n).  ND = feature values of the far site carried by the columns: 2 for a two-site bond
+// (4 far-bond indices per tile), 1 for the single-site form (columns (k_local; l, m), 8 far-bond indices per tile)
+template <int L, int HALF, int ND>
+__device__ __forceinline__ void fh_epilogue_tile(uint32_t taddr, const float (&pp)[4], const float (&ek)[8 / ND], float (&facc)[L]) {
   constexpr int NCH = (16 * L) / 32;          // 16-column chunks per half
+  constexpr int PER = 2 * L * ND;             // columns per far-bond index
 #pragma unroll
   for (int cb = 0; cb < NCH; ++cb) {
     float v[16];
@@ -387,15 +389,49 @@ __device__ __forceinline__ void fh_epilogue_tile(uint32_t taddr, const float (&p
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const int col = (HALF * NCH + cb) * 16 + e;
-      const int kl = col / (4 * L), r = col % (4 * L), l = r >> 2, mn = r & 3;
+      const int kl = col / PER, r = col % PER, l = r / (2 * ND), mn = r % (2 * ND);
       facc[l] = fmaf(v[e], pp[mn] * ek[kl], facc[l]);
     }
   }
 }
 
+// single-site form of the forward (the logits of a bond that is still the product of its two sites, i.e. before the first
+// update: f[t,l] = sum_{m,i,j} phi[t,m] e_near[t,i] S[l,m,i,j] z[t,j] with z the cached environment on the other side of
+// the SAME site -- half the columns of the merged bond, half the MMAs).  Images of the special node S (L,2,Ds,Ds):
+// [tile j][chunk q][hi|lo][160 rows (k_local; l, m) x 64 near-bond indices]; dir > 0: near index = S's third index
 template <int L>
+__global__ void forward_prep_site_kernel(const float* __restrict__ S, uint8_t* __restrict__ bimg, const int32_t* __restrict__ maxbits,
+                                         int Ds, int dir, int ntiles, int nchunks) {
+  constexpr int NT = 16 * L, IMG_BYTES = NT * 128, PER = 2 * L;
+  const int ex = -bond_exponent(maxbits);
+  const int64_t total = (int64_t)ntiles * nchunks * NT * 8;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % 8);
+    const int col = (int)((e / 8) % NT);
+    const int64_t jq = e / (8 * NT);
+    const int q = (int)(jq % nchunks), j = (int)(jq / nchunks);
+    const int kl = col / PER, r = col % PER, l = r >> 1, m = r & 1;
+    const int k = 8 * j + kl;
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = q * FH_KCH + ch * 8 + u;
+      float v = 0.f;
+      if (k < Ds && i < Ds) v = dir > 0 ? S[((int64_t)(l * 2 + m) * Ds + i) * Ds + k] : S[((int64_t)(l * 2 + m) * Ds + k) * Ds + i];
+      v = scale_pow2(v, ex);
+      hi[u] = __float2half_rn(v);
+      lo[u] = __float2half_rn(v - __half2float(hi[u]));
+    }
+    uint8_t* img = bimg + jq * (2 * IMG_BYTES) + k128_chunk_off(col, ch);
+    *reinterpret_cast<uint4*>(img) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(img + IMG_BYTES) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+template <int L, int ND>
 __global__ void __launch_bounds__(FH_THREADS, 1) forward_h_kernel(FwdHArgs a) {
-  constexpr int NT = 16 * L;
+  constexpr int NT = 16 * L, KPT = 8 / ND;             // KPT: far-bond indices per tile
   constexpr int IMG_BYTES = NT * 128;                // one (hi | lo) B image: NT rows x 64 fp16
   constexpr int STAGE_BYTES = 2 * IMG_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * NT <= 64 ? 64 : 2 * NT <= 128 ? 128 : 2 * NT <= 256 ? 256 : 512;
@@ -414,7 +450,7 @@ __global__ void __launch_bounds__(FH_THREADS, 1) forward_h_kernel(FwdHArgs a) {
   const int64_t t0 = (int64_t)blockIdx.x * FT_TM;
   const int dn = __ldg(a.d_near), df = __ldg(a.d_far);
   const int nchunks = (dn + FH_KCH - 1) / FH_KCH;
-  const int ntiles = (df + 3) / 4;
+  const int ntiles = (df + KPT - 1) / KPT;
 
   if (tid == 0) {
     for (int s = 0; s < FT_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -519,30 +555,41 @@ __global__ void __launch_bounds__(FH_THREADS, 1) forward_h_kernel(FwdHArgs a) {
     float pp[4] = {0.f, 0.f, 0.f, 0.f};
     if (live) {
       const float2 p1 = __ldg(reinterpret_cast<const float2*>(a.phi_near) + tg);
-      const float2 p2 = __ldg(reinterpret_cast<const float2*>(a.phi_far) + tg);
-      pp[0] = p1.x * p2.x; pp[1] = p1.x * p2.y; pp[2] = p1.y * p2.x; pp[3] = p1.y * p2.y;   // index m*2+n
+      if (ND == 2) {
+        const float2 p2 = __ldg(reinterpret_cast<const float2*>(a.phi_far) + tg);
+        pp[0] = p1.x * p2.x; pp[1] = p1.x * p2.y; pp[2] = p1.y * p2.x; pp[3] = p1.y * p2.y;   // index m*2+n
+      } else {
+        pp[0] = p1.x; pp[1] = p1.y;                                                             // index m
+      }
     }
     float facc[L];
 #pragma unroll
     for (int l = 0; l < L; ++l) facc[l] = 0.f;
     // far-environment entries of my row, fetched two tiles ahead: the load latency (~1 us) must not sit between the
     // accumulator becoming ready and its drain
+    struct EK { float4 v[KPT / 4]; };
     auto load_e = [&](int j) {
-      float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live && j < ntiles && 4 * j < Ds) e = __ldg(reinterpret_cast<const float4*>(a.e_far + tg * Ds + 4 * j));
+      EK e;
+#pragma unroll
+      for (int u = 0; u < KPT / 4; ++u) {
+        e.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && j < ntiles && KPT * j + 4 * u < Ds) e.v[u] = __ldg(reinterpret_cast<const float4*>(a.e_far + tg * Ds + KPT * j + 4 * u));
+      }
       return e;
     };
-    float4 e_cur = load_e(0), e_nxt = load_e(1);
+    EK e_cur = load_e(0), e_nxt = load_e(1);
     for (int j = 0; j < ntiles; ++j) {
       const int b = j & 1;
-      const float4 e_nn = load_e(j + 2);
-      const float ek[4] = {e_cur.x, e_cur.y, e_cur.z, e_cur.w};
+      const EK e_nn = load_e(j + 2);
+      float ek[KPT];
+#pragma unroll
+      for (int u = 0; u < KPT / 4; ++u) { ek[4 * u] = e_cur.v[u].x; ek[4 * u + 1] = e_cur.v[u].y; ek[4 * u + 2] = e_cur.v[u].z; ek[4 * u + 3] = e_cur.v[u].w; }
       e_cur = e_nxt; e_nxt = e_nn;
       mbar_wait(&acc_full[b], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * NT);
-      if (half == 0) fh_epilogue_tile<L, 0>(taddr, pp, ek, facc);
-      else fh_epilogue_tile<L, 1>(taddr, pp, ek, facc);
+      if (half == 0) fh_epilogue_tile<L, 0, ND>(taddr, pp, ek, facc);
+      else fh_epilogue_tile<L, 1, ND>(taddr, pp, ek, facc);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[b]);
@@ -604,10 +651,10 @@ int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_
     const size_t smem_h = forward_h_smem<10>();
     static bool attr_h = false;
     if (!attr_h) {
-      TRMPS_CUDA_OK(cudaFuncSetAttribute(forward_h_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+      TRMPS_CUDA_OK(cudaFuncSetAttribute(forward_h_kernel<10, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
       attr_h = true;
     }
-    forward_h_kernel<10><<<(unsigned)ceil_div64(B, FT_TM), FH_THREADS, smem_h, st>>>(h);
+    forward_h_kernel<10, 2><<<(unsigned)ceil_div64(B, FT_TM), FH_THREADS, smem_h, st>>>(h);
     TRMPS_LAUNCH_OK("forward_h_kernel");
     return TRMPS_OK;
   }
@@ -625,6 +672,39 @@ int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_
   }
   forward_tc_kernel<10><<<(unsigned)ceil_div64(B, FT_TM), FT_THREADS, smem, st>>>(a);
   TRMPS_LAUNCH_OK("forward_tc_kernel");
+  return TRMPS_OK;
+}
+
+// single-site form of the first forward of a bond update (see forward_prep_site_kernel): special = the special node at the near
+// site, e_far = the cached environment on the other side of the same site, d_far = the bond between the two sites
+bool forward_site_tc_supported(int Ds, int L) { return option_value(1) == 0 && forward_tc_supported(Ds, L, 2); }
+
+int launch_forward_site_tc(const float* e_near, const float* e_far, const float* phi_near, const float* special, int dir, float* bimg,
+                           float* f_out, int64_t B, int Ds, int L, const int32_t* d_near, const int32_t* d_far, cudaStream_t st) {
+  if (B <= 0) return TRMPS_OK;
+  if (!forward_site_tc_supported(Ds, L)) {
+    set_error("forward_site_tc: unsupported shape Ds=%d L=%d", Ds, L);
+    return TRMPS_E_ARG;
+  }
+  const int ntiles = (Ds + 7) / 8, nchunks = (Ds + FH_KCH - 1) / FH_KCH;
+  uint8_t* img = reinterpret_cast<uint8_t*>(bimg);
+  int32_t* maxbits = reinterpret_cast<int32_t*>(img + (size_t)ntiles * nchunks * 2 * 16 * L * 128);
+  TRMPS_CUDA_OK(cudaMemsetAsync(maxbits, 0, sizeof(int32_t), st));
+  absmax_kernel<<<148, 256, 0, st>>>(special, (int64_t)2 * L * Ds * Ds, maxbits);
+  TRMPS_LAUNCH_OK("absmax_kernel");
+  forward_prep_site_kernel<10><<<296, 256, 0, st>>>(special, img, maxbits, Ds, dir, ntiles, nchunks);
+  TRMPS_LAUNCH_OK("forward_prep_site_kernel");
+  FwdHArgs h;
+  h.e_near = e_near; h.e_far = e_far; h.phi_near = phi_near; h.phi_far = phi_near; h.bimg = img; h.maxbits = maxbits;
+  h.f = f_out; h.B = B; h.Ds = Ds; h.d_near = d_near; h.d_far = d_far; h.nchunks_max = nchunks;
+  const size_t smem_h = forward_h_smem<10>();
+  static bool attr_h = false;
+  if (!attr_h) {
+    TRMPS_CUDA_OK(cudaFuncSetAttribute(forward_h_kernel<10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+    attr_h = true;
+  }
+  forward_h_kernel<10, 1><<<(unsigned)ceil_div64(B, FT_TM), FH_THREADS, smem_h, st>>>(h);
+  TRMPS_LAUNCH_OK("forward_h_kernel");
   return TRMPS_OK;
 }
 

@@ -53,6 +53,7 @@ ProfScope::~ProfScope() {
 static int g_grad_impl = 0;   // 0 = tcgen05 3xTF32, 1 = FP32 SIMT
 static int g_fwd_impl = 0;    // same for the forward contraction
 static int g_chain_impl = 0;  // 0 = fused tcgen05 chain for inference when Ds <= 32, 1 = per-site FP32 SIMT steps
+static int g_fwd_site = 1;    // first forward of a two-site update in its single-site form (needs the cached environment of the same site: trmps_sweep_init_env / sweeps provide it)
 static int g_env_impl = 0;    // environments of the sweep: 0 = tcgen05 chain from / to HBM, 1 = per-site FP32 SIMT steps
 int option_value(int option) { return option == 0 ? g_grad_impl : option == 1 ? g_fwd_impl : g_chain_impl; }
 
@@ -292,7 +293,8 @@ static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const Bond
 
 // gradient step(s) with Armijo backtracking and accept/revert on the bond matrix in bondM (optimizer.py:239-264,
 // baseoptimizer.py:299-332); shared by the two-site and the single-site update
-static int do_update_bond(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, cudaStream_t st) {
+static int do_update_bond(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, cudaStream_t st,
+                          bool site_form = false) {
   const int L = s->L;
   const int64_t RC = (int64_t)2 * s->Ds * 2 * L * s->Ds;
   float* w = s->work;
@@ -300,7 +302,16 @@ static int do_update_bond(const trmps_sweep* s, const trmps_layout& lay, const B
   const bool hess = opt->use_hessian && s->loss_kind == TRMPS_LOSS_SOFTMAX_XENT;
   const float* delta = hess ? w + lay.deltaM : w + lay.gradM;
   int rc;
-  if ((rc = do_forward(s, lay, g, w + lay.bondM, st))) return rc;
+  if (site_form) {
+    // the bond is still the product of its two sites: its logits are those of the special node alone with the cached
+    // environment on the other side of the same site -- half the contraction (2 B L d Dl Dm instead of 2 B L d^2 Dl Dr flops)
+    ProfScope ps(PROF_FORWARD, st);
+    const int64_t stride = s->B * (int64_t)s->Ds;
+    const float* e_same = g.dir > 0 ? s->envR + stride * g.near_site : s->envL + stride * g.near_site;
+    if ((rc = launch_forward_site_tc(g.e_near, e_same, w + lay.phi2, s->special, g.dir, w + lay.bimg, w + lay.fpart, s->B, s->Ds, L,
+                                     g.d_near, g.d_mid, st)))
+      return rc;
+  } else if ((rc = do_forward(s, lay, g, w + lay.bondM, st))) return rc;
   const int nupd = opt->updates_per_step > 0 ? opt->updates_per_step : 0;
   for (int u = 0; u < nupd; ++u) {                                  // baseoptimizer.py:324-332
     if ((rc = do_gradient(s, lay, g, opt, u == 0, st))) return rc;
@@ -343,7 +354,8 @@ static int do_bond_step(const trmps_sweep* s, const trmps_layout& lay, int site,
   int rc;
   if ((rc = phi_pair(s, lay, g, st))) return rc;
   if ((rc = do_merge(s, lay, g, st))) return rc;
-  if ((rc = do_update_bond(s, lay, g, opt, st))) return rc;
+  const bool site_form = g_fwd_site != 0 && g_fwd_impl == 0 && forward_site_tc_supported(s->Ds, s->L);
+  if ((rc = do_update_bond(s, lay, g, opt, st, site_form))) return rc;
   {
     ProfScope ps(PROF_SVD, st);
     if ((rc = svd_split(s, lay, g, opt, st))) return rc;
@@ -484,6 +496,7 @@ extern "C" int trmps_set_option(int32_t option, int32_t value) {
   if (option == 2 && (value == 0 || value == 1 || value == 2)) { g_chain_impl = value; return TRMPS_OK; }
   if (option == 3 && value >= 0 && value <= 3) { set_flat_variant(value); return TRMPS_OK; }
   if (option == 4 && (value == 0 || value == 1)) { g_env_impl = value; return TRMPS_OK; }
+  if (option == 5 && (value == 0 || value == 1)) { g_fwd_site = value; return TRMPS_OK; }
   set_error("trmps_set_option: unknown option %d / value %d", option, value);
   return TRMPS_E_ARG;
 }
