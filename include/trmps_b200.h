@@ -183,7 +183,10 @@ int         trmps_set_option(int32_t option, int32_t value); /* option 0: gradie
                                                             option 3: tile shape of the flat datasource kernel (development switch, 0 = default);
                                                             option 4: environment chain of the sweep (initial build and the advance after every
                                                             split): 0 = tcgen05 (the inference chain started from / writing to HBM) while the
-                                                            chain's rounding-bias estimate stays below 9e-5, 1 = FP32 SIMT steps */
+                                                            chain's rounding-bias estimate stays below 9e-5, 1 = FP32 SIMT steps;
+                                                            option 5: first forward of a two-site update: 1 (default) = single-site form
+                                                            (special node x cached environment of the same site, half the contraction; needs the
+                                                            environments trmps_sweep_init_env / the sweeps keep), 0 = on the merged bond */
 int64_t     trmps_launch_count(void);                   /* kernels launched by this library so far (process-wide) */
 
 /* optional device-side timing of the kernels a sweep launches (CUDA events on the caller's stream; replaces the

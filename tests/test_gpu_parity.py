@@ -217,9 +217,18 @@ def test_split_matches_lapack(direction, D, max_size, impl):
 
 
 # --------------------------------------------------------------------------------------------- full bond update / sweep
+@pytest.fixture
+def site_form(request):
+    # trmps_set_option(5, v): first forward of the update in its single-site form (default) or on the merged bond
+    nat.set_option(5, request.param)
+    yield request.param
+    nat.set_option(5, 1)
+
+
+@pytest.mark.parametrize("site_form", [1, 0], indirect=True)
 @pytest.mark.parametrize("loss", [o.SOFTMAX_XENT, o.SQUARED])
 @pytest.mark.parametrize("updates", [1, 3])
-def test_bond_step_matches_oracle(loss, updates):
+def test_bond_step_matches_oracle(loss, updates, site_form):
     N, B, L, loc = 8, 400, 10, 3
     pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=41, loc=loc)
     st = make_state(N, B, L, 24, nodes, loc, phi, lab, loss=loss)
