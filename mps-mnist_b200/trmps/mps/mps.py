@@ -161,7 +161,7 @@ class MPS(object):
         if self.nodes_list is None:
             raise RuntimeError("call prepare() before using the MPS (mps.py:189)")
         if self._device_weights is None:
-            nat.require_gpu(0)
+            nat.require_gpu(torch.cuda.current_device())
             Ds = dev.bond_stride(self.nodes_list, self._special_node_loc, self.d_output)
             self._device_weights = dev.DeviceWeights(self.nodes_list, self._special_node_loc, self.d_output, Ds,
                                                      torch.device('cuda', torch.cuda.current_device()))
