@@ -163,7 +163,7 @@ int launch_grad(const float* e_near, const float* e_far, const float* phi_near, 
                 int64_t B, int Ds, int L, bool squared, cudaStream_t st);
 int launch_sum_parts(const float* part, int nparts, int64_t n, float* out, cudaStream_t st);
 int launch_grad_tc(const float* e_near, const float* e_far, const float* phi_near, const float* sres, float* gpart, int gsplit,
-                   int64_t B, int Ds, int L, cudaStream_t st, float* dbg = nullptr);
+                   int64_t B, int Ds, int L, cudaStream_t st, float* dbg = nullptr, bool squared = false);
 int grad_tc_splits(int64_t B, int Ds, int L, int sms);
 bool grad_h_supported(int64_t B, int Ds, int L);
 int launch_grad_h(const float* e_near, const float* e_far, const float* phi_near, const float* sres, float* gpart, int gsplit,

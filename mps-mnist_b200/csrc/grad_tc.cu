@@ -134,6 +134,8 @@ __device__ __forceinline__ uint32_t tile_off(int mn, int k, int atoms_per_k) {
   return (uint32_t)((kg * atoms_per_k + blk) * TC_ATOM + k4 * 128 + ((c32 ^ k4) << 5) + half * 16);
 }
 
+// SQ: the diagonal Hessian (optimizer.py:229-237): the same contraction with squared operands, sum_t hres[t,(l,n)] (phi e_near)^2 e_far^2
+template <bool SQ>
 __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -208,7 +210,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
       const int k = ksub + KS * r;
       {
         float4 hi, lo;
-        const float vx = ra[r].x * pa[r], vy = ra[r].y * pa[r], vz = ra[r].z * pa[r], vw = ra[r].w * pa[r];
+        float vx = ra[r].x * pa[r], vy = ra[r].y * pa[r], vz = ra[r].z * pa[r], vw = ra[r].w * pa[r];
+        if (SQ) { vx *= vx; vy *= vy; vz *= vz; vw *= vw; }
         hi.x = tf32_round(vx); hi.y = tf32_round(vy); hi.z = tf32_round(vz); hi.w = tf32_round(vw);
         lo.x = vx - hi.x; lo.y = vy - hi.y; lo.z = vz - hi.z; lo.w = vw - hi.w;
         const uint32_t off = tile_off(4 * q4, k, TC_TM / 32);
@@ -217,7 +220,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
       }
       {
         float4 hi, lo;
-        const float vx = rb[r].x * pb[r], vy = rb[r].y * pb[r], vz = rb[r].z * pb[r], vw = rb[r].w * pb[r];
+        float vx = rb[r].x * pb[r], vy = rb[r].y * pb[r], vz = rb[r].z * pb[r], vw = rb[r].w * pb[r];
+        if (SQ) { vx *= rb[r].x; vy *= rb[r].y; vz *= rb[r].z; vw *= rb[r].w; }          // the weight (hres) enters once
         hi.x = tf32_round(vx); hi.y = tf32_round(vy); hi.z = tf32_round(vz); hi.w = tf32_round(vw);
         lo.x = vx - hi.x; lo.y = vy - hi.y; lo.z = vz - hi.z; lo.w = vw - hi.w;
         const uint32_t off = tile_off(4 * q4, k, TC_TN / 32);
@@ -324,7 +328,7 @@ int grad_tc_splits(int64_t B, int Ds, int L, int sms) {
 }
 
 int launch_grad_tc(const float* e_near, const float* e_far, const float* phi_near, const float* sres, float* gpart, int gsplit,
-                   int64_t B, int Ds, int L, cudaStream_t st, float* dbg) {
+                   int64_t B, int Ds, int L, cudaStream_t st, float* dbg, bool squared) {
   GradTcArgs g;
   g.e_near = e_near; g.e_far = e_far; g.phi_near = phi_near; g.sres = sres; g.gpart = gpart;
   g.B = B; g.Ds = Ds; g.L = L; g.R = 2 * Ds; g.Cc = 2 * L * Ds; g.dbg = dbg;
@@ -332,11 +336,13 @@ int launch_grad_tc(const float* e_near, const float* e_far, const float* phi_nea
   g.imgs_per_split = ceil_div64(per, TC_KCH) * TC_KCH;
   static bool attr_set = false;
   if (!attr_set) {
-    TRMPS_CUDA_OK(cudaFuncSetAttribute(grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    TRMPS_CUDA_OK(cudaFuncSetAttribute(grad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    TRMPS_CUDA_OK(cudaFuncSetAttribute(grad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
   dim3 grid((unsigned)((g.Cc + TC_TN - 1) / TC_TN), (unsigned)((g.R + TC_TM - 1) / TC_TM), (unsigned)gsplit);
-  grad_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g);
+  if (squared) grad_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g);
+  else grad_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g);
   TRMPS_LAUNCH_OK("grad_tc_kernel");
   return TRMPS_OK;
 }

@@ -278,8 +278,15 @@ static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const Bond
     if ((rc = allreduce_sum(s->comm, w + lay.gradM, RC + 4, st))) return rc;
   }
   if (hess) {
-    if ((rc = launch_grad(g.e_near, g.e_far, w + lay.phi2, w + lay.hres, w + lay.gpart, lay.gsplit, s->B, Ds, L, true, st))) return rc;
-    if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit, RC, w + lay.hessM, st))) return rc;
+    // diagonal Hessian: the gradient contraction with squared operands (optimizer.py:229-237), on the same tensor-core kernel
+    ProfScope ps(PROF_GRAD, st);
+    if (g_grad_impl != 1) {
+      if ((rc = launch_grad_tc(g.e_near, g.e_far, w + lay.phi2, w + lay.hres, w + lay.gpart, lay.gsplit_tc, s->B, Ds, L, st, nullptr, true))) return rc;
+      if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit_tc, RC, w + lay.hessM, st))) return rc;
+    } else {
+      if ((rc = launch_grad(g.e_near, g.e_far, w + lay.phi2, w + lay.hres, w + lay.gpart, lay.gsplit, s->B, Ds, L, true, st))) return rc;
+      if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit, RC, w + lay.hessM, st))) return rc;
+    }
     if ((rc = allreduce_sum(s->comm, w + lay.hessM, RC, st))) return rc;
   }
   float* scal = w + lay.scal;
