@@ -127,6 +127,25 @@ def run_preprocess_case(seed=21, count=26, size=40):
     return rec
 
 
+def run_linreg_case(loss, N=9, L=4, total=230, iterations=5, lr=0.05, seed=31):
+    """The reference's own MPS._lin_reg (mps.py:331-399; sqMPS._cost_for_lin_reg squaredDistanceMPS.py:29-30) fed by the
+    reference's own MPSDatasource.next_training_data_batch(100) (preprocessing.py:165-208) on `total` seeded samples, so the
+    third minibatch wraps around the end of the set.  tf.train.GradientDescentOptimizer is the shim's numerical derivative
+    of the reference's cost graph (tf1_shim._GradientDescentOptimizer), i.e. nothing of the oracle's closed-form gradient."""
+    from preprocessing.preprocessing import MPSDatasource                # reference code
+    pix, lab = o.synthetic_batch(N, total, L, seed=seed)                 # (N, total), (total, L)
+    data = np.ascontiguousarray(np.swapaxes(o.feature_map(pix, o.FM_ONE_X), 0, 1))      # (total, N, 2)
+    ds = MPSDatasource.__new__(MPSDatasource)
+    ds._training_data, ds._test_data = (data, lab), (data[:40], lab[:40])
+    ds._swapped_test_data = ds._swapped_training_data = None
+    ds.current_index = 0
+    network = (sqMPS if loss == 1 else MPS)(2, L, N)
+    network._lin_reg(ds, iterations, lr)
+    return dict(data=data, labels=lab, weight=np.asarray(network.weight), bias=np.asarray(network.bias),
+                loc=np.int32(network._special_node_loc), next_index=np.int32(ds.current_index),
+                cfg=np.array([N, L, total, iterations, lr, loss, seed], dtype=np.float64))
+
+
 def write_idx(dirname, name, payload, dims, magic):
     import gzip
     header = magic.to_bytes(4, "big") + b"".join(int(x).to_bytes(4, "big") for x in dims)
@@ -176,6 +195,12 @@ def main():
         rec = run_preprocess_case()
     np.savez_compressed(os.path.join(OUT, "ref_preprocess.npz"), **rec)
     print("ref_preprocess", rec["phi1_shrink"].shape, rec["phi1_full"].shape)
+    for loss, name in ((0, "ref_linreg_xent"), (1, "ref_linreg_squared")):
+        sink = io.StringIO()
+        with contextlib.redirect_stdout(sink):
+            rec = run_linreg_case(loss)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print(name, "weight", rec["weight"].shape, "loc", int(rec["loc"]), "next", int(rec["next_index"]))
     for name, cfg in CASES.items():
         sink = io.StringIO()
         with contextlib.redirect_stdout(sink):            # the reference prints a lot

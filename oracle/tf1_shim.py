@@ -25,6 +25,7 @@ class _Ctx(object):
         self.feed = feed
         self.cache = {}
         self.bind = {}      # values of the symbolic loop variables of the while_loop iteration being evaluated
+        self.var_override = {}      # Variable uid -> value used instead of its stored one (numerical gradients)
 
 
 class Tensor(object):
@@ -130,15 +131,77 @@ def placeholder_with_default(input, shape, name=None):
     return _Placeholder(dtype, shape, input, name)
 
 
+_VARIABLES = []
+
+
 class Variable(Tensor):
+    """Mutable: tf.train.GradientDescentOptimizer.minimize (below) updates .value; an evaluation context may override it
+    (the numerical gradient evaluates the cost at perturbed values)."""
+
     def __init__(self, initial_value, dtype=None, trainable=True, name=None):
-        value = np.asarray(initial_value, dtype=dtype if dtype is not None else None)
-        self.dtype = value.dtype
-        Tensor.__init__(self, lambda c: value, name)
+        if isinstance(initial_value, Tensor):
+            initial_value = initial_value._eval(_Ctx({}))
+        self.value = np.array(initial_value, dtype=dtype if dtype is not None else None)
+        self.dtype = self.value.dtype
+        Tensor.__init__(self, lambda c: c.var_override.get(self._uid, self.value), name)
+        _VARIABLES.append(self)
 
 
 def global_variables_initializer():
     return _const(None)
+
+
+class _GradientDescentOptimizer(object):
+    """tf.train.GradientDescentOptimizer(lr).minimize(cost): var <- var - lr * d cost / d var for every Variable the cost
+    depends on.  TensorFlow differentiates the graph symbolically; this stand-in has no graph to differentiate (a Tensor is
+    a closure), so the derivative of the REFERENCE'S OWN cost graph is taken numerically: central differences in float64
+    (variables and fed values cast up; step 1e-6 relative to max(1, |v|)), accurate to ~1e-9 -- far below the float32
+    round-off of the update itself.  Slow (two cost evaluations per parameter), meant for small golden-vector cases."""
+
+    def __init__(self, learning_rate, *a, **k):
+        self.lr = float(learning_rate)
+
+    def minimize(self, cost, *a, **k):
+        lr = self.lr
+
+        def fn(c):
+            feed64 = {k_: (np.asarray(v, dtype=np.float64) if np.asarray(v).dtype.kind == "f" else v) for k_, v in c.feed.items()}
+
+            def cost_at(override):
+                ctx = _Ctx(feed64)
+                ctx.var_override = override
+                return float(np.asarray(cost._eval(ctx), dtype=np.float64))
+
+            base = {v._uid: v.value.astype(np.float64) for v in _VARIABLES}
+            f0 = cost_at(base)
+            grads = {}
+            for v in _VARIABLES:
+                x = base[v._uid]
+                g = np.zeros_like(x)
+                # does the cost depend on this variable at all?
+                # (a pseudo-random direction: a uniform shift of all logits leaves a softmax cost unchanged)
+                probe = dict(base)
+                probe[v._uid] = x + 1e-3 * np.random.RandomState(v._uid % (2 ** 31)).standard_normal(x.shape)
+                if cost_at(probe) == f0:
+                    continue
+                it = np.nditer(x, flags=["multi_index"])
+                for _ in it:
+                    idx = it.multi_index
+                    h = 1e-6 * max(1.0, abs(x[idx]))
+                    xp, xm = x.copy(), x.copy()
+                    xp[idx] += h; xm[idx] -= h
+                    op, om = dict(base), dict(base)
+                    op[v._uid], om[v._uid] = xp, xm
+                    g[idx] = (cost_at(op) - cost_at(om)) / (2 * h)
+                grads[v._uid] = g
+            for v in _VARIABLES:
+                if v._uid in grads:
+                    v.value = (v.value.astype(np.float64) - lr * grads[v._uid]).astype(v.dtype)
+            return None
+        return Tensor(fn)
+
+
+train = types.SimpleNamespace(GradientDescentOptimizer=_GradientDescentOptimizer)
 
 
 class TensorShape(object):
@@ -362,7 +425,6 @@ class _NotAvailable(object):
         raise NotImplementedError("not provided by the NumPy TF1 shim (outside the hot path)")
 
 
-train = types.SimpleNamespace(GradientDescentOptimizer=_NotAvailable)
 
 
 class _Dummy(object):

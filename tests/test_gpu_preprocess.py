@@ -240,6 +240,25 @@ def test_linreg_pretrain_matches_oracle(loss, N, total, start, iters):
     assert rel(W.cpu().numpy(), wantW) < max(20 * rel(W32, wantW), 2e-6)       # no worse than fp32 NumPy
 
 
+@pytest.mark.parametrize("name,loss", [("ref_linreg_xent", o.SOFTMAX_XENT), ("ref_linreg_squared", o.SQUARED)])
+def test_linreg_pretrain_matches_reference_code_golden(name, loss):
+    """trmps_linreg_pretrain and MPS.prepare(data_source) against what the reference's own MPS._lin_reg produced under the
+    shim (tests/golden/ref_linreg_*.npz, oracle/make_golden_from_reference.py::run_linreg_case)."""
+    from trmps import MPS, sqMPS, MPSDatasource
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    N, L, iters, lr = int(g["cfg"][0]), int(g["cfg"][1]), int(g["cfg"][3]), float(g["cfg"][4])
+    data, labels = g["data"].astype(np.float32), g["labels"].astype(np.float32)
+    W, b = dev.linreg_pretrain(torch.from_numpy(data).cuda(), torch.from_numpy(labels).cuda(), 0, iters, lr, loss)
+    assert rel(W.cpu().numpy(), g["weight"][:, 0, :]) < 2e-6 and rel(b.cpu().numpy(), g["bias"]) < 2e-6
+    class InMemory(MPSDatasource):
+        _use_cache_dir = False
+    ds = InMemory(_training_data=(data, labels), _test_data=(data[:40], labels[:40]))
+    net = (sqMPS if loss == o.SQUARED else MPS)(2, L, N)
+    net.prepare(ds, iterations=iters, learning_rate=lr)
+    assert rel(net.weight, g["weight"]) < 2e-6 and rel(net.bias, g["bias"]) < 2e-6
+    assert net._special_node_loc == int(g["loc"]) and ds.current_index == int(g["next_index"])
+
+
 def rel(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)

@@ -11,7 +11,7 @@ import trmps_oracle as o
 ALL_NPZ = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 GOLDEN = [p for p in ALL_NPZ if not os.path.basename(p).startswith("ref_")]     # written by oracle/make_golden.py
 REF_GOLDEN = [p for p in ALL_NPZ if os.path.basename(p).startswith("ref_")      # written by the REFERENCE code under oracle/tf1_shim.py
-              and os.path.basename(p) not in ("ref_preprocess.npz", "ref_fashion.npz")]   # (sweep cases; the datasource cases have their own tests)
+              and os.path.basename(p) not in ("ref_preprocess.npz", "ref_fashion.npz", "ref_linreg_xent.npz", "ref_linreg_squared.npz")]   # (sweep cases; the others have their own tests)
 GOLDEN_DIR = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -230,3 +230,20 @@ def test_fashion_oracle_matches_reference_loader_code():
     u = np.arange(256)
     assert np.array_equal((u / 255.0).astype(np.float32), u.astype(np.float32) / np.float32(255))
     assert np.any((u / 255.0).astype(np.float32) != o.scale_uint8(u.astype(np.uint8)))       # and differs from the TF loader's
+
+
+@pytest.mark.parametrize("name,loss", [("ref_linreg_xent", o.SOFTMAX_XENT), ("ref_linreg_squared", o.SQUARED)])
+def test_lin_reg_oracle_matches_reference_code_run_under_tf_shim(name, loss):
+    """tests/golden/ref_linreg_*.npz: the reference's own MPS._lin_reg / sqMPS._cost_for_lin_reg (mps.py:327-399,
+    squaredDistanceMPS.py:29-30) fed by its own MPSDatasource.next_training_data_batch, with tf.train.GradientDescentOptimizer
+    standing for a float64 central-difference derivative of the reference's cost graph -- so the oracle's closed-form
+    gradient, the batch of 100, the wrap-around and the weight layout (N, d-1, L) are pinned by reference code."""
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    N, L, total, iters, lr = int(g["cfg"][0]), int(g["cfg"][1]), int(g["cfg"][2]), int(g["cfg"][3]), float(g["cfg"][4])
+    assert total < iters * 100                                          # the set is read more than once (wrap-around)
+    W, b, nxt = o.lin_reg(g["data"], g["labels"], 0, iters, lr, loss)
+    assert g["weight"].shape == (N, 1, L) and nxt == int(g["next_index"])
+    assert np.abs(W - g["weight"][:, 0, :]).max() < 2e-7 * np.abs(W).max()        # float32 storage of the reference's variables
+    assert np.abs(b - g["bias"]).max() < 2e-7 * max(np.abs(b).max(), np.abs(W).max())
+    site = int(np.unravel_index(g["weight"].argmax(), g["weight"].shape)[0])     # mps.py:392-399
+    assert int(g["loc"]) == min(max(site, 1), N - 2)
