@@ -423,13 +423,23 @@ struct JacArgs {
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float s) {
   s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); return fmaf(a.w, b.w, s);
 }
-__device__ __forceinline__ void rot4(float4& x, float4& y, float sn, float tau) {
+// packed FP32 (FFMA2, sm_100): two lanes of a float2 per instruction -- the Jacobi phase is bound by instruction issue
+// and latency of a single warp per scheduler, so the long-row arithmetic (inner products, rotations) is issued in pairs
+__device__ __forceinline__ float2 dot4_2(const float4& a, const float4& b, float2 s) {
+  s = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), s);
+  return __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), s);
+}
+__device__ __forceinline__ void rot2(float& x0, float& x1, float& y0, float& y1, float2 sn, float2 nsn, float2 tau, float2 ntau) {
   // Rutishauser's form x' = x - s (y + tau x), y' = y + s (x - tau y): norm-preserving in FP32 even when cos rounds to 1
-  float u, w;
-  u = x.x; w = y.x; x.x = fmaf(-sn, fmaf(tau, u, w), u); y.x = fmaf(sn, fmaf(-tau, w, u), w);
-  u = x.y; w = y.y; x.y = fmaf(-sn, fmaf(tau, u, w), u); y.y = fmaf(sn, fmaf(-tau, w, u), w);
-  u = x.z; w = y.z; x.z = fmaf(-sn, fmaf(tau, u, w), u); y.z = fmaf(sn, fmaf(-tau, w, u), w);
-  u = x.w; w = y.w; x.w = fmaf(-sn, fmaf(tau, u, w), u); y.w = fmaf(sn, fmaf(-tau, w, u), w);
+  const float2 u = make_float2(x0, x1), w = make_float2(y0, y1);
+  const float2 xn = __ffma2_rn(nsn, __ffma2_rn(tau, u, w), u);
+  const float2 yn = __ffma2_rn(sn, __ffma2_rn(ntau, w, u), w);
+  x0 = xn.x; x1 = xn.y; y0 = yn.x; y1 = yn.y;
+}
+__device__ __forceinline__ void rot4(float4& x, float4& y, float sn, float tau) {
+  const float2 s2 = make_float2(sn, sn), ns2 = make_float2(-sn, -sn), t2 = make_float2(tau, tau), nt2 = make_float2(-tau, -tau);
+  rot2(x.x, x.y, y.x, y.y, s2, ns2, t2, nt2);
+  rot2(x.z, x.w, y.z, y.w, s2, ns2, t2, nt2);
 }
 
 // ---- hand-over of the row blocks without a cluster-wide barrier: the rows are written into the next CTA's shared memory
@@ -543,9 +553,9 @@ __device__ __forceinline__ void jacobi_apply(JRow<WIDE>& x, JRow<WIDE>& y, const
 
 template <bool WIDE>
 __device__ __forceinline__ float jdot(const JRow<WIDE>& x, const JRow<WIDE>& y) {
-  float s = dot4(x.lo, y.lo, 0.f);
-  if (WIDE) s += dot4(x.hi, y.hi, 0.f);
-  return s;
+  float2 s = dot4_2(x.lo, y.lo, make_float2(0.f, 0.f));
+  if (WIDE) s = dot4_2(x.hi, y.hi, s);
+  return s.x + s.y;
 }
 
 // Two steps on four rows held in registers: (xa,ya), (xb,yb), then (xa,yb), (xb,ya).  All six inner products of the four
@@ -578,6 +588,121 @@ __device__ __forceinline__ float jacobi_quad(JRow<WIDE>& xa, JRow<WIDE>& xb, JRo
     jacobi_apply<WIDE>(xa, yb, r3);
     jacobi_apply<WIDE>(xb, ya, r4);
     worst = fmaxf(worst, fmaxf(r3.relg, r4.relg));
+  }
+  return worst;
+}
+
+// Four steps on EIGHT rows held in registers (x_0..3 from one block, y_0..3 from the other): step s rotates the pairs
+// (x_i, y_(i+s)%4), i.e. all 16 cross pairs in the minimum of four steps.  All 28 inner products of the eight rows are formed
+// ONCE per phase and reduced with a transposing butterfly (31 shuffles: after the five levels lane l holds the total of
+// product l); from then on the 8 x 8 Gram matrix is carried through the rotations by linearity, distributed over the lanes
+// as 2 x 2 blocks: with the y rows relabelled after every step so that the rotated pairs are always (x_i, y_i), lane 4i+j
+// holds H_ij = [[x_i.x_j, x_i.y_j], [y_i.x_j, y_i.y_j]] and a step is H_ij <- J_i H_ij J_j^T -- lane-local, only the two
+// rotations are fetched from the diagonal lanes 5i, 5j, which computed them (the four angles of a step are computed at
+// once, one per lane, instead of one after the other on all lanes).  The relabelling y_i <- y_(i+1) moves three entries of
+// every block to a fixed neighbour lane.  A step's dependent chain is angle -> fetch -> block update -> relabel (~250
+// cycles) instead of products -> 5-level reduction -> angle per two steps, and a phase is 53 instructions per rotation
+// instead of 105: the Jacobi kernel runs one warp per scheduler, so both count.  Squared norms (the diagonal of H) are
+// carried as before (al' = al - t ga).  Returns, per lane, the largest |cos| it rotated away (diagonal lanes).
+template <bool WIDE>
+__device__ __forceinline__ float jacobi_oct(JRow<WIDE> (&xs)[4], JRow<WIDE> (&ys)[4], float tol, int lane) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[4 * i + j] = jdot<WIDE>(xs[i], ys[j]);
+  {
+    int k = 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = i + 1; j < 4; ++j) { v[k] = jdot<WIDE>(xs[i], xs[j]); v[k + 6] = jdot<WIDE>(ys[i], ys[j]); ++k; }
+  }
+  v[28] = v[29] = v[30] = v[31] = 0.f;
+  // transposing butterfly: level `off` halves the number of live values; the lane keeps the half selected by its own bit
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = up ? v[k] : v[k + off];
+      const float keep = up ? v[k + off] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  const float tot = v[0];                       // total of product `lane`
+  // block (i, j) of this lane (lanes 16..31 mirror 0..15) and where its entries come from
+  const int bi = (lane >> 2) & 3, bj = lane & 3;
+  const int lo_ = min(bi, bj), hi_ = max(bi, bj);
+  const int tri = ((lo_ * (7 - lo_)) >> 1) + (hi_ - lo_ - 1) + (bi == bj ? 1 : 0);   // (0,1)(0,2)(0,3)(1,2)(1,3)(2,3) -> 0..5 (diagonal: any valid lane)
+  float hxy = __shfl_sync(0xffffffffu, tot, 4 * bi + bj);
+  float hyx = __shfl_sync(0xffffffffu, tot, 4 * bj + bi);
+  float hxx = __shfl_sync(0xffffffffu, tot, 16 + tri);
+  float hyy = __shfl_sync(0xffffffffu, tot, 22 + tri);
+  const bool dg = bi == bj;
+  {
+    const bool b0 = (bi & 1) != 0, b1 = (bi & 2) != 0;
+    const float ax01 = b0 ? xs[1].nrm : xs[0].nrm, ax23 = b0 ? xs[3].nrm : xs[2].nrm;
+    const float ay01 = b0 ? ys[1].nrm : ys[0].nrm, ay23 = b0 ? ys[3].nrm : ys[2].nrm;
+    const float ax = b1 ? ax23 : ax01, ay = b1 ? ay23 : ay01;
+    hxx = dg ? ax : hxx;
+    hyy = dg ? ay : hyy;
+  }
+  const int src_i = 5 * bi, src_j = 5 * bj;
+  const int nb_xy = 4 * bi + ((bj + 1) & 3), nb_yx = 4 * ((bi + 1) & 3) + bj, nb_yy = 4 * ((bi + 1) & 3) + ((bj + 1) & 3);
+  float worst = 0.f;
+#pragma unroll
+  for (int st = 0; st < 4; ++st) {
+    // the angle of pair i on lane 5i, from the unnormalised products: two dependent MUFU levels on the chain of the steps
+    // (rsqrt(d^2 + 4 g^2), rsqrt((1 + cos 2 theta) / 2)); tan(theta / 2) and |cos| between the rows are off the chain
+    const float al = hxx, be = hyy, ga = hxy;
+    const float d = be - al, g2 = ga + ga;
+    const float big = fmaxf(al, be), small = fminf(al, be);
+    const float relg0 = fabsf(ga) * rsqrt_fast(al * be);
+    const bool rot = small > 1e-30f && small > 1e-24f * big && relg0 > tol;
+    const float rh = rsqrt_fast(fmaf(d, d, g2 * g2));
+    const float xx = fmaf(0.5f * fabsf(d), rh, 0.5f);
+    const float rc = rsqrt_fast(xx);
+    const float cc0 = xx * rc;
+    const float s0 = ((d >= 0.f) ? ga : -ga) * rh * rc;
+    const float sn = rot ? s0 : 0.f, cs = rot ? cc0 : 1.f;
+    const float tau = rot ? s0 * rcp_fast(1.f + cc0) : 0.f;
+    const float tg = rot ? s0 * rc * ga : 0.f;
+    worst = fmaxf(worst, (dg && rot) ? relg0 : 0.f);
+    // the four rotations of the step, to every lane (selects only: a per-lane branch here costs a divergence stack round trip)
+    float sk[4], tk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sk[k] = __shfl_sync(0xffffffffu, sn, 5 * k);
+    const float dxx = fmaxf(hxx - tg, 0.f), dyy = fmaxf(hyy + tg, 0.f);
+    if (st < 3) {
+      // H <- J_i H J_j^T, then relabel y_i <- y_(i+1)
+      const float s_i = __shfl_sync(0xffffffffu, sn, src_i), c_i = __shfl_sync(0xffffffffu, cs, src_i);
+      const float s_j = __shfl_sync(0xffffffffu, sn, src_j), c_j = __shfl_sync(0xffffffffu, cs, src_j);
+      const float txx = fmaf(c_i, hxx, -s_i * hyx), txy = fmaf(c_i, hxy, -s_i * hyy);
+      const float tyx = fmaf(s_i, hxx, c_i * hyx), tyy = fmaf(s_i, hxy, c_i * hyy);
+      const float nxx = fmaf(c_j, txx, -s_j * txy), nxy = fmaf(s_j, txx, c_j * txy);
+      const float nyx = fmaf(c_j, tyx, -s_j * tyy), nyy = fmaf(s_j, tyx, c_j * tyy);
+      hxx = dg ? dxx : nxx;
+      hxy = __shfl_sync(0xffffffffu, dg ? 0.f : nxy, nb_xy);
+      hyx = __shfl_sync(0xffffffffu, dg ? 0.f : nyx, nb_yx);
+      hyy = __shfl_sync(0xffffffffu, dg ? dyy : nyy, nb_yy);
+    } else {
+      hxx = dg ? dxx : hxx; hyy = dg ? dyy : hyy;
+    }
+    // the rows: pair k is (x_k, y_(k+st)%4)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tk[k] = __shfl_sync(0xffffffffu, tau, 5 * k);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      rot4(xs[k].lo, ys[(k + st) & 3].lo, sk[k], tk[k]);
+      if (WIDE) rot4(xs[k].hi, ys[(k + st) & 3].hi, sk[k], tk[k]);
+    }
+  }
+  // carried squared norms back to the rows: after the last step lane 5i holds those of x_i and of y_(i+3)%4
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    xs[k].nrm = __shfl_sync(0xffffffffu, hxx, 5 * k);
+    ys[(k + 3) & 3].nrm = __shfl_sync(0xffffffffu, hyy, 5 * k);
   }
   return worst;
 }
@@ -707,8 +832,48 @@ __global__ void __launch_bounds__(16 * BR) split_jacobi_kernel(JacArgs a) {
           __syncthreads();
         }
         const int nph = r == 0 ? JPH_ALL : JPH_CROSS;
+        int ph0 = 0;
+        if constexpr (BR == 8) {
+          // cross-block pairs: two phases of jacobi_oct by warps 0 and 1 (x rows 4w..4w+3 of block A stay in registers, the y
+          // rows of block B alternate between the two warps); the pairs inside the blocks (round 0) follow on the 2 x 2 path
+          ph0 = JPH_CROSS;
+          JRow<WIDE> xs[4], ys[4];
+          const bool last_is_oct = r != 0;
+          // warps 2 and 3 shadow warps 0 and 1 (same loads, same arithmetic, nothing stored): a per-thread branch around
+          // jacobi_oct would make every one of its shuffles divergence-checked (WARPSYNC + ENDCOLLECTIVE per SHFL)
+          const int ow = warp & 1;
+          const bool owner = warp < 2;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) xs[k].load(base + (size_t)(4 * ow + k) * JLD, lane);
+#pragma unroll 1
+          for (int t = 0; t < 2; ++t) {
+            const int y0 = JB + 4 * ((ow + t) & 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ys[k].load(base + (size_t)(y0 + k) * JLD, lane);
+            const float w8 = jacobi_oct<WIDE>(xs, ys, a.tol, lane);
+            worst = owner ? fmaxf(worst, w8) : worst;
+            if (t == 1 && last_is_oct && xchg) {
+              if (owner) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) send(ys[k], y0 + k);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) send(xs[k], 4 * ow + k);
+              }
+            } else {
+              if (owner) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ys[k].store(base + (size_t)(y0 + k) * JLD, lane);
+                if (t == 1) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) xs[k].store(base + (size_t)(4 * ow + k) * JLD, lane);
+                }
+              }
+              __syncthreads();
+            }
+          }
+        }
         JRow<WIDE> xa, xb, ya, yb;
-        for (int ph = 0; ph < nph; ++ph) {
+        for (int ph = ph0; ph < nph; ++ph) {
           const uchar4 rw = tab_rows[ph][warp];
           const int fl = tab_flags[ph][warp];
           if (fl & 1) { xa.load(base + (size_t)rw.x * JLD, lane); xb.load(base + (size_t)rw.y * JLD, lane); }
