@@ -604,19 +604,31 @@ __device__ __forceinline__ float jacobi_quad(JRow<WIDE>& xa, JRow<WIDE>& xb, JRo
 // cycles) instead of products -> 5-level reduction -> angle per two steps, and a phase is 53 instructions per rotation
 // instead of 105: the Jacobi kernel runs one warp per scheduler, so both count.  Squared norms (the diagonal of H) are
 // carried as before (al' = al - t ga).  Returns, per lane, the largest |cos| it rotated away (diagonal lanes).
-template <bool WIDE>
-__device__ __forceinline__ float jacobi_oct(JRow<WIDE> (&xs)[4], JRow<WIDE> (&ys)[4], float tol, int lane) {
+// Every lane holds ONE float4 of each row: at n <= 128 a warp covers the whole rows (PAIR = false); beyond, two warps share
+// the eight rows, one column half each (PAIR = true): they add their partial products through shared memory behind a
+// two-warp named barrier (fixed order lo + hi: both get the same bits), run the small Gram chain redundantly and rotate
+// their own halves -- the long-row FFMA2s of a phase, which bound it, are spread over all four schedulers of the SM.
+__device__ __forceinline__ float2 dot4p(const float4& a, const float4& b) {
+  const float2 s = __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(0.f, 0.f)));
+  return s;
+}
+template <bool PAIR>
+__device__ __forceinline__ float jacobi_oct(float4 (&xs)[4], float4 (&ys)[4], float (&xn)[4], float (&yn)[4], float tol, int lane,
+                                            float* exch_mine, const float* exch_other, int bar_id, bool first_half) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[4 * i + j] = jdot<WIDE>(xs[i], ys[j]);
+    for (int j = 0; j < 4; ++j) { const float2 d2 = dot4p(xs[i], ys[j]); v[4 * i + j] = d2.x + d2.y; }
   {
     int k = 16;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = i + 1; j < 4; ++j) { v[k] = jdot<WIDE>(xs[i], xs[j]); v[k + 6] = jdot<WIDE>(ys[i], ys[j]); ++k; }
+      for (int j = i + 1; j < 4; ++j) {
+        const float2 dx = dot4p(xs[i], xs[j]), dy = dot4p(ys[i], ys[j]);
+        v[k] = dx.x + dx.y; v[k + 6] = dy.x + dy.y; ++k;
+      }
   }
   v[28] = v[29] = v[30] = v[31] = 0.f;
   // transposing butterfly: level `off` halves the number of live values; the lane keeps the half selected by its own bit
@@ -630,7 +642,13 @@ __device__ __forceinline__ float jacobi_oct(JRow<WIDE> (&xs)[4], JRow<WIDE> (&ys
       v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
     }
   }
-  const float tot = v[0];                       // total of product `lane`
+  float tot = v[0];                             // total of product `lane` (over this warp's columns)
+  if (PAIR) {
+    exch_mine[lane] = tot;
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    const float other = exch_other[lane];
+    tot = first_half ? tot + other : other + tot;
+  }
   // block (i, j) of this lane (lanes 16..31 mirror 0..15) and where its entries come from
   const int bi = (lane >> 2) & 3, bj = lane & 3;
   const int lo_ = min(bi, bj), hi_ = max(bi, bj);
@@ -642,8 +660,8 @@ __device__ __forceinline__ float jacobi_oct(JRow<WIDE> (&xs)[4], JRow<WIDE> (&ys
   const bool dg = bi == bj;
   {
     const bool b0 = (bi & 1) != 0, b1 = (bi & 2) != 0;
-    const float ax01 = b0 ? xs[1].nrm : xs[0].nrm, ax23 = b0 ? xs[3].nrm : xs[2].nrm;
-    const float ay01 = b0 ? ys[1].nrm : ys[0].nrm, ay23 = b0 ? ys[3].nrm : ys[2].nrm;
+    const float ax01 = b0 ? xn[1] : xn[0], ax23 = b0 ? xn[3] : xn[2];
+    const float ay01 = b0 ? yn[1] : yn[0], ay23 = b0 ? yn[3] : yn[2];
     const float ax = b1 ? ax23 : ax01, ay = b1 ? ay23 : ay01;
     hxx = dg ? ax : hxx;
     hyy = dg ? ay : hyy;
@@ -655,16 +673,19 @@ __device__ __forceinline__ float jacobi_oct(JRow<WIDE> (&xs)[4], JRow<WIDE> (&ys
   for (int st = 0; st < 4; ++st) {
     // the angle of pair i on lane 5i, from the unnormalised products: two dependent MUFU levels on the chain of the steps
     // (rsqrt(d^2 + 4 g^2), rsqrt((1 + cos 2 theta) / 2)); tan(theta / 2) and |cos| between the rows are off the chain
+    // (products scaled by 1 / max norm, which only depends on the carried norms: tiny rows of a rank-deficient bond would
+    // underflow in d^2 + 4 g^2 otherwise)
     const float al = hxx, be = hyy, ga = hxy;
-    const float d = be - al, g2 = ga + ga;
     const float big = fmaxf(al, be), small = fminf(al, be);
-    const float relg0 = fabsf(ga) * rsqrt_fast(al * be);
+    const float inv = rcp_fast(big);
+    const float relg0 = fabsf(ga) * rsqrt_fast(al) * rsqrt_fast(be);
     const bool rot = small > 1e-30f && small > 1e-24f * big && relg0 > tol;
+    const float d = (be - al) * inv, gs = ga * inv, g2 = gs + gs;
     const float rh = rsqrt_fast(fmaf(d, d, g2 * g2));
     const float xx = fmaf(0.5f * fabsf(d), rh, 0.5f);
     const float rc = rsqrt_fast(xx);
     const float cc0 = xx * rc;
-    const float s0 = ((d >= 0.f) ? ga : -ga) * rh * rc;
+    const float s0 = ((d >= 0.f) ? gs : -gs) * rh * rc;
     const float sn = rot ? s0 : 0.f, cs = rot ? cc0 : 1.f;
     const float tau = rot ? s0 * rcp_fast(1.f + cc0) : 0.f;
     const float tg = rot ? s0 * rc * ga : 0.f;
@@ -694,15 +715,14 @@ __device__ __forceinline__ float jacobi_oct(JRow<WIDE> (&xs)[4], JRow<WIDE> (&ys
     for (int k = 0; k < 4; ++k) tk[k] = __shfl_sync(0xffffffffu, tau, 5 * k);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      rot4(xs[k].lo, ys[(k + st) & 3].lo, sk[k], tk[k]);
-      if (WIDE) rot4(xs[k].hi, ys[(k + st) & 3].hi, sk[k], tk[k]);
+      rot4(xs[k], ys[(k + st) & 3], sk[k], tk[k]);
     }
   }
   // carried squared norms back to the rows: after the last step lane 5i holds those of x_i and of y_(i+3)%4
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    xs[k].nrm = __shfl_sync(0xffffffffu, hxx, 5 * k);
-    ys[(k + 3) & 3].nrm = __shfl_sync(0xffffffffu, hyy, 5 * k);
+    xn[k] = __shfl_sync(0xffffffffu, hxx, 5 * k);
+    yn[(k + 3) & 3] = __shfl_sync(0xffffffffu, hyy, 5 * k);
   }
   return worst;
 }
@@ -729,6 +749,7 @@ __global__ void __launch_bounds__(16 * BR) split_jacobi_kernel(JacArgs a) {
   __shared__ __align__(8) uint64_t rx_bar[2];                  // rx_bar[b]: the two blocks of buffer b have arrived
   __shared__ uchar4 tab_rows[JPH_ALL][JWARPS];
   __shared__ unsigned char tab_flags[JPH_ALL][JWARPS];         // 1: load x rows, 2: store x rows, 4: first half only
+  __shared__ float oct_x[2][2][32];                            // partial inner products of the two column halves of an oct
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int crank = (int)cluster.block_rank();
   const int n = 2 * *a.d_near, R = a.R;
@@ -837,37 +858,62 @@ __global__ void __launch_bounds__(16 * BR) split_jacobi_kernel(JacArgs a) {
           // cross-block pairs: two phases of jacobi_oct by warps 0 and 1 (x rows 4w..4w+3 of block A stay in registers, the y
           // rows of block B alternate between the two warps); the pairs inside the blocks (round 0) follow on the 2 x 2 path
           ph0 = JPH_CROSS;
-          JRow<WIDE> xs[4], ys[4];
+          // WIDE: warps w and w + 2 share an oct, one column half each.  Otherwise warps 2 and 3 shadow warps 0 and 1 (same
+          // loads, same arithmetic, nothing stored): a per-thread branch around jacobi_oct would make every one of its
+          // shuffles divergence-checked (WARPSYNC + ENDCOLLECTIVE per SHFL)
           const bool last_is_oct = r != 0;
-          // warps 2 and 3 shadow warps 0 and 1 (same loads, same arithmetic, nothing stored): a per-thread branch around
-          // jacobi_oct would make every one of its shuffles divergence-checked (WARPSYNC + ENDCOLLECTIVE per SHFL)
-          const int ow = warp & 1;
-          const bool owner = warp < 2;
+          const int ow = warp & 1, half = WIDE ? (warp >> 1) : 0;
+          const bool owner = WIDE || warp < 2;
+          const int coff = 128 * half + lane * 4;
+          constexpr int NPOS = JRow<WIDE>::NPOS;
+          float4 xs[4], ys[4];
+          float xn[4], yn[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) xs[k].load(base + (size_t)(4 * ow + k) * JLD, lane);
+          for (int k = 0; k < 4; ++k) {
+            const float* pr = base + (size_t)(4 * ow + k) * JLD;
+            xs[k] = *reinterpret_cast<const float4*>(pr + coff); xn[k] = pr[NPOS];
+          }
 #pragma unroll 1
           for (int t = 0; t < 2; ++t) {
             const int y0 = JB + 4 * ((ow + t) & 1);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ys[k].load(base + (size_t)(y0 + k) * JLD, lane);
-            const float w8 = jacobi_oct<WIDE>(xs, ys, a.tol, lane);
+            for (int k = 0; k < 4; ++k) {
+              const float* pr = base + (size_t)(y0 + k) * JLD;
+              ys[k] = *reinterpret_cast<const float4*>(pr + coff); yn[k] = pr[NPOS];
+            }
+            const float w8 = jacobi_oct<WIDE>(xs, ys, xn, yn, a.tol, lane, &oct_x[ow][half][0], &oct_x[ow][half ^ 1][0], 1 + ow, half == 0);
             worst = owner ? fmaxf(worst, w8) : worst;
-            if (t == 1 && last_is_oct && xchg) {
-              if (owner) {
+            const bool hand_over = t == 1 && last_is_oct && xchg;
+            if (owner) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) send(ys[k], y0 + k);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) send(xs[k], 4 * ow + k);
+              for (int k = 0; k < 4; ++k) {
+                float* pr = base + (size_t)(y0 + k) * JLD;
+                *reinterpret_cast<float4*>(pr + coff) = ys[k];
+                if (half == 0 && lane == 0) pr[NPOS] = yn[k];
               }
-            } else {
-              if (owner) {
+              if (t == 1) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ys[k].store(base + (size_t)(y0 + k) * JLD, lane);
-                if (t == 1) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) xs[k].store(base + (size_t)(4 * ow + k) * JLD, lane);
+                for (int k = 0; k < 4; ++k) {
+                  float* pr = base + (size_t)(4 * ow + k) * JLD;
+                  *reinterpret_cast<float4*>(pr + coff) = xs[k];
+                  if (half == 0 && lane == 0) pr[NPOS] = xn[k];
                 }
               }
+            }
+            if (hand_over) {
+              // every row of the round goes to its next owner as one bulk copy, once both column halves are in shared memory
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              if (WIDE) asm volatile("bar.sync %0, 64;" ::"r"(1 + ow) : "memory");
+              else __syncwarp();
+              if (owner && half == 0 && lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int ry = y0 + k - JB, rx = 4 * ow + k;
+                  bulk_row_to_cta(rdst1 + (uint32_t)ry * ROW_STRIDE, smem_addr(base + (size_t)(y0 + k) * JLD), ROW_BYTES, rbar1);
+                  bulk_row_to_cta(rdst0 + (uint32_t)rx * ROW_STRIDE, smem_addr(base + (size_t)rx * JLD), ROW_BYTES, rbar0);
+                }
+              }
+            } else {
               __syncthreads();
             }
           }
