@@ -905,13 +905,13 @@ __global__ void __launch_bounds__(16 * BR) split_jacobi_kernel(JacArgs a) {
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               if (WIDE) asm volatile("bar.sync %0, 64;" ::"r"(1 + ow) : "memory");
               else __syncwarp();
-              if (owner && half == 0 && lane == 0) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const int ry = y0 + k - JB, rx = 4 * ow + k;
-                  bulk_row_to_cta(rdst1 + (uint32_t)ry * ROW_STRIDE, smem_addr(base + (size_t)(y0 + k) * JLD), ROW_BYTES, rbar1);
-                  bulk_row_to_cta(rdst0 + (uint32_t)rx * ROW_STRIDE, smem_addr(base + (size_t)rx * JLD), ROW_BYTES, rbar0);
-                }
+              if (owner && half == 0 && lane < 8) {
+                // lanes 0..3: the y rows, lanes 4..7: the x rows (eight copies issued at once instead of one after the other)
+                const int k = lane & 3;
+                const bool isx = lane >= 4;
+                const int row = isx ? 4 * ow + k : y0 + k;
+                const uint32_t dst = isx ? rdst0 + (uint32_t)row * ROW_STRIDE : rdst1 + (uint32_t)(row - JB) * ROW_STRIDE;
+                bulk_row_to_cta(dst, smem_addr(base + (size_t)row * JLD), ROW_BYTES, isx ? rbar0 : rbar1);
               }
             } else {
               __syncthreads();
