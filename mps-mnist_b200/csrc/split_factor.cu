@@ -730,6 +730,196 @@ __device__ __forceinline__ float jacobi_oct(float4 (&xs)[4], float4 (&ys)[4], fl
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------------ 2b. Cholesky in a cluster
+// The same factorisation G = L L^T (R = L^T) spread over one thread-block cluster, right-looking by column blocks of 16:
+// CTA J owns columns 16J .. 16J+15 of L (rows >= 16J), keeps that block of the trailing matrix in shared memory and
+//   * for K = 0 .. J-1 waits for column block K of L (rows >= 16J), which CTA K pushes into THIS CTA's shared memory as one
+//     bulk copy signalling an mbarrier here, and subtracts its contribution (rank-16 update; all earlier blocks are usually
+//     in before block J-1 arrives, so only the last update is on the critical path);
+//   * factorises its 16 x 16 diagonal block (one warp, registers + shuffles, the pivot rule of the single-CTA kernel),
+//     solves the rows below and pushes rows >= 16J' of the result to every CTA J' > J (no flow control: a CTA has room for
+//     all the pieces it will ever receive, at most J (n - 16J) rows <= 147 KB);
+//   * writes its 16 rows of R = L^T in FP32 (scaled) and their squared norms; CTA 0 ranks the rows (de Rijk ordering).
+// The critical path is 16 x (diagonal block + solve + push + one update) instead of the whole n^3/3 on one SM:
+// measured 208 -> see DESIGN.md us at 240 x 240.
+constexpr int CC_T = 256, CC_LD = 18;          // row stride of a block in shared memory (doubles): 144 B rows, conflict-free LDS.128
+
+struct CholCArgs {
+  const double* G; float* Rf; int R; const int32_t* d_near; float* scale; int32_t* rowmap; int csize;
+};
+
+size_t chol_cluster_smem(int R) {
+  size_t best = 0;
+  for (int J = 0; 16 * J < R; ++J) best = max(best, (size_t)J * (size_t)(R - 16 * J));
+  return ((size_t)SP_NMAX + best) * CC_LD * sizeof(double);
+}
+
+__global__ void __launch_bounds__(CC_T) split_chol_cluster_kernel(CholCArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) double ccs[];
+  __shared__ __align__(8) uint64_t pbar[16];
+  __shared__ double rinv_s[CW];
+  __shared__ double red[CC_T / 32];
+  __shared__ float nrm_part[CW][SP_NMAX / 32];
+  __shared__ float nrm_all[SP_NMAX];                       // CTA 0: squared norms of all rows of R
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int J = (int)cluster.block_rank();
+  const int n = 2 * *a.d_near, R = a.R;
+  const int NB = (n + CW - 1) / CW;
+  const bool active = J < NB;
+  const int r0 = CW * J, nrows = active ? n - r0 : 0, w = active ? min(CW, n - r0) : 0;
+  double* A = ccs;                                         // A[li * CC_LD + c] = (trailing matrix / L)[r0 + li][r0 + c]
+  double* P = ccs + (size_t)SP_NMAX * CC_LD;               // piece K: rows r0 .. n-1 of column block K, nrows x CC_LD
+  // largest diagonal entry -> pivot threshold and the power-of-two scale of the FP32 copy (every CTA, same bits)
+  double dmax = 0.0;
+  for (int i = tid; i < n; i += CC_T) dmax = fmax(dmax, __ldcg(&a.G[(size_t)i * R + i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  if (lane == 0) red[warp] = dmax;
+  if (tid < CW && tid < J) {
+    mbar_init_cta(&pbar[tid], 1);
+  }
+  __syncthreads();
+  dmax = 0.0;
+  for (int q = 0; q < CC_T / 32; ++q) dmax = fmax(dmax, red[q]);
+  const double tolp = (double)n * 2.3e-16 * dmax;
+  const double sq_tolp = sqrt(tolp > 0.0 ? tolp : 1e-300), inv_dmax = dmax > 0.0 ? 1.0 / dmax : 0.0, rs_dmax = dmax > 0.0 ? rsqrt(dmax) : 0.0;
+  int ex = 0;
+  if (dmax > 0.0) frexp(sqrt(dmax), &ex);
+  const double inv_scale = ldexp(1.0, -ex);
+  if (active && tid < J) mbar_expect_tx_cta(&pbar[tid], (uint32_t)nrows * CC_LD * 8u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  // own block of G (stored in full and symmetric: column r0 + c read as row r0 + c, unit stride in li)
+  for (int e = tid; e < CW * SP_NMAX; e += CC_T) {
+    const int c = e / SP_NMAX, li = e % SP_NMAX;
+    if (li < nrows) A[li * CC_LD + c] = c < w ? __ldcg(&a.G[(size_t)(r0 + c) * R + r0 + li]) : 0.0;
+  }
+  __syncthreads();
+  cluster_arrive_release();
+  cluster_wait_acquire();
+  if (active) {
+    // ---- contributions of the column blocks to the left
+    for (int K = 0; K < J; ++K) {
+      mbar_wait_cta(&pbar[K], 0);
+      const double* Pk = P + (size_t)K * nrows * CC_LD;
+      if (tid < nrows) {
+        double pr[CW], acc[CW];
+#pragma unroll
+        for (int t = 0; t < CW; t += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(&Pk[tid * CC_LD + t]);
+          pr[t] = v.x; pr[t + 1] = v.y;
+        }
+#pragma unroll
+        for (int c = 0; c < CW; ++c) {
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int t = 0; t < CW; t += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(&Pk[c * CC_LD + t]);      // L[r0 + c][16 K + t], broadcast
+            s0 = fma(pr[t], v.x, s0); s1 = fma(pr[t + 1], v.y, s1);
+          }
+          acc[c] = s0 + s1;
+        }
+#pragma unroll
+        for (int c = 0; c < CW; ++c) A[tid * CC_LD + c] -= acc[c];
+      }
+    }
+    __syncthreads();
+    // ---- diagonal block: one warp, lane r holds row r, 16 dependent steps (see split_chol_kernel)
+    if (warp == 0) {
+      const int r = lane & 15;
+      double d[CW];
+#pragma unroll
+      for (int c = 0; c < CW; ++c) d[c] = (r < nrows) ? A[r * CC_LD + c] : 0.0;
+#pragma unroll
+      for (int c = 0; c < CW; ++c) {
+        const double piv = __shfl_sync(0xffffffffu, d[c], c);
+        const bool drop = !(piv > tolp) || c >= w;
+        const double rinv = drop ? 0.0 : rsqrt_seeded(piv * inv_dmax) * rs_dmax;
+        const double lkk = drop ? sq_tolp : piv * rinv;
+        const double l = r == c ? lkk : d[c] * rinv;
+        d[c] = l;
+#pragma unroll
+        for (int cc = c + 1; cc < CW; ++cc) {
+          const double t = __shfl_sync(0xffffffffu, l, cc);
+          d[cc] = fma(-l, t, d[cc]);
+        }
+        if (lane == 0) rinv_s[c] = rinv;
+      }
+      if (lane < CW && r < nrows) {
+#pragma unroll
+        for (int c = 0; c < CW; ++c) A[r * CC_LD + c] = c <= r ? d[c] : 0.0;
+      }
+    }
+    __syncthreads();
+    // ---- rows below: forward substitution with the factor of the diagonal block
+    if (tid >= CW && tid < nrows) {
+      double p[CW];
+#pragma unroll
+      for (int c = 0; c < CW; c += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(&A[tid * CC_LD + c]);
+        p[c] = v.x; p[c + 1] = v.y;
+      }
+#pragma unroll
+      for (int c = 0; c < CW; ++c) {
+        const double l = p[c] * rinv_s[c];
+        p[c] = l;
+#pragma unroll
+        for (int cc = c + 1; cc < CW; ++cc) p[cc] = fma(-l, A[cc * CC_LD + c], p[cc]);
+      }
+#pragma unroll
+      for (int c = 0; c < CW; c += 2) *reinterpret_cast<double2*>(&A[tid * CC_LD + c]) = make_double2(p[c], p[c + 1]);
+    }
+    // ---- push rows >= 16 J' to every CTA J' > J (nearest first: it is the one waiting)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+      const int Jd = J + 1 + lane;
+      if (Jd < NB) {
+        const int nr_d = n - CW * Jd;
+        const uint32_t dst = map_to_cta(smem_addr(P + (size_t)J * nr_d * CC_LD), Jd);
+        const uint32_t bar = map_to_cta(smem_addr(&pbar[J]), Jd);
+        bulk_row_to_cta(dst, smem_addr(A + (size_t)(CW * (Jd - J)) * CC_LD), (uint32_t)nr_d * CC_LD * 8u, bar);
+      }
+    }
+    // ---- rows r0 .. r0+w-1 of R = L^T in FP32 (scaled), zeros left of the block and beyond n; their squared norms
+#pragma unroll
+    for (int u = 0; u < CW * SP_NMAX / CC_T; ++u) {
+      const int e = tid + u * CC_T, c = e / SP_NMAX, j = e % SP_NMAX;
+      float f = 0.f;
+      if (c < w && j < R) {
+        if (j >= r0 && j < n) f = (float)(A[(j - r0) * CC_LD + c] * inv_scale);
+        a.Rf[(size_t)(r0 + c) * R + j] = f;
+      }
+      float sq = f * f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      if (lane == 0) nrm_part[c][j / 32] = sq;
+    }
+    __syncthreads();
+    if (tid < w) {
+      float sq = 0.f;
+#pragma unroll
+      for (int q = 0; q < SP_NMAX / 32; ++q) sq += nrm_part[tid][q];
+      *cluster.map_shared_rank(&nrm_all[r0 + tid], 0) = sq;
+    }
+  }
+  // nobody leaves while a copy out of its shared memory may be in flight; the norms are with CTA 0
+  cluster_arrive_release();
+  cluster_wait_acquire();
+  if (J == 0) {
+    if (tid < n) {
+      const float sp = nrm_all[tid];
+      int rank = 0;
+      for (int o = 0; o < n; ++o) {
+        const float so = nrm_all[o];
+        rank += (so > sp) || (so == sp && o < tid);
+      }
+      a.rowmap[rank] = tid;
+    }
+    if (tid == 0) { a.scale[0] = (float)ldexp(1.0, ex); a.scale[1] = (float)dmax; }
+  }
+}
+
 // Inside a CTA the 32 rows of its two blocks are rotated by 8 warps with 2 x 2 register blocking: a warp holds two rows
 // x_a, x_b in registers over several phases, fetches two rows y_a, y_b per phase from shared memory and rotates
 // (x_a,y_a), (x_b,y_b), then (x_a,y_b), (x_b,y_a): four rotations per two rows moved through shared memory (a row per
@@ -1412,7 +1602,37 @@ int split_factor(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& 
   ga.KS = (chunks + per - 1) / per;
   split_gram_kernel<<<dim3(ntiles, ga.KS), 256, 0, st>>>(ga);
   TRMPS_LAUNCH_OK("split_gram_kernel");
-  // 2. Cholesky
+  // 2. Cholesky: spread over a cluster (split_impl 0, when the device can schedule the cluster), else on one SM
+  const int chol_csize = R <= 16 ? 1 : R <= 32 ? 2 : R <= 64 ? 4 : R <= 128 ? 8 : 16;
+  static int chol_cluster_ok[17] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+  const size_t chol_smem = chol_cluster_smem(SP_NMAX);
+  if (chol_cluster_ok[chol_csize] < 0) {
+    chol_cluster_ok[chol_csize] = 0;
+    if (cudaFuncSetAttribute(split_chol_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(split_chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem) == cudaSuccess) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(chol_csize); q.blockDim = dim3(CC_T); q.dynamicSmemBytes = chol_smem;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = chol_csize; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, split_chol_cluster_kernel, &q) == cudaSuccess && ncl > 0) chol_cluster_ok[chol_csize] = 1;
+    }
+    (void)cudaGetLastError();
+  }
+  if (opt->split_impl == 0 && chol_cluster_ok[chol_csize] == 1) {
+    CholCArgs cc;
+    cc.G = w.G; cc.Rf = w.Rf; cc.R = R; cc.d_near = g.d_near; cc.scale = w.scale; cc.rowmap = w.rowmap; cc.csize = chol_csize;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(chol_csize); cfg.blockDim = dim3(CC_T); cfg.dynamicSmemBytes = chol_smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = chol_csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, split_chol_cluster_kernel, cc));
+    count_launch();
+  } else {
   CholArgs ca;
   ca.G = w.G; ca.Rd = w.Rd; ca.Rf = w.Rf; ca.R = R; ca.d_near = g.d_near; ca.scale = w.scale; ca.rowmap = w.rowmap; ca.dbg = s->work + lay.red + 8;
   {
@@ -1425,6 +1645,7 @@ int split_factor(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& 
     split_chol_kernel<<<1, CT, smem, st>>>(ca);
   }
   TRMPS_LAUNCH_OK("split_chol_kernel");
+  }
   // 3. Jacobi in one cluster
   JacArgs ja;
   ja.Rf = w.Rf; ja.R = R; ja.rowmap = w.rowmap; ja.d_near = g.d_near; ja.X = w.X; ja.sig = w.sig; ja.iscal = s->iwork;
