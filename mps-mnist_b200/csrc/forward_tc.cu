@@ -358,8 +358,12 @@ __global__ void forward_prep_h_kernel(const float* __restrict__ M, uint8_t* __re
 struct FwdHArgs {
   const float* e_near; const float* e_far; const float* phi_near; const float* phi_far; const uint8_t* bimg;
   const int32_t* maxbits; float* f; int64_t B; int Ds; const int32_t* d_near; const int32_t* d_far; int nchunks_max;
+  // the image tiles beyond the last full wave are split by columns over `parts` CTAs each (tpp column tiles per CTA): their
+  // partial logits go to pscr, the last CTA of an image tile to arrive (pcnt) adds them in a fixed order
+  int n_full, parts, tpp; float* pscr; int32_t* pcnt;
 };
 
+constexpr int FH_PARTS_MAX = 6, FH_TAIL_MAX = 160, FH_PCNT = 256;   // column parts per tail tile, SMs sized for, counter words
 constexpr int FH_THREADS = 320;        // warps 0-7: epilogue (TMEM lane quadrant x column half), 8: MMA issuer, 9: B loader
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -447,10 +451,20 @@ __global__ void __launch_bounds__(FH_THREADS, 1) forward_h_kernel(FwdHArgs a) {
   float* xch = reinterpret_cast<float*>(rexp + FT_TM);               // [128][L] partial logits of the second column half
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Ds = a.Ds;
-  const int64_t t0 = (int64_t)blockIdx.x * FT_TM;
+  int* s_last = reinterpret_cast<int*>(xch + FT_TM * L);
   const int dn = __ldg(a.d_near), df = __ldg(a.d_far);
   const int nchunks = (dn + FH_KCH - 1) / FH_KCH;
-  const int ntiles = (df + KPT - 1) / KPT;
+  const int ntiles_all = (df + KPT - 1) / KPT;
+  // image tile and column-tile range [j0, j0 + ntiles) of this CTA
+  int rt = (int)blockIdx.x, part = 0, j0 = 0, ntiles = ntiles_all;
+  const bool partial = (int)blockIdx.x >= a.n_full && a.parts > 1;
+  if (partial) {
+    const int u = (int)blockIdx.x - a.n_full;
+    rt = a.n_full + u / a.parts; part = u % a.parts;
+    j0 = min(part * a.tpp, ntiles_all);
+    ntiles = min(ntiles_all, j0 + a.tpp) - j0;
+  }
+  const int64_t t0 = (int64_t)rt * FT_TM;
 
   if (tid == 0) {
     for (int s = 0; s < FT_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -512,7 +526,7 @@ __global__ void __launch_bounds__(FH_THREADS, 1) forward_h_kernel(FwdHArgs a) {
           const int s = it % FT_STAGES, ph = (it / FT_STAGES) & 1;
           if (it >= FT_STAGES) mbar_wait(&b_empty[s], (uint32_t)(ph ^ 1));
           mbar_expect_tx(&b_full[s], STAGE_BYTES);
-          bulk_g2s(bst + s * STAGE_BYTES, a.bimg + ((int64_t)j * a.nchunks_max + q) * STAGE_BYTES, STAGE_BYTES, &b_full[s]);
+          bulk_g2s(bst + s * STAGE_BYTES, a.bimg + ((int64_t)(j0 + j) * a.nchunks_max + q) * STAGE_BYTES, STAGE_BYTES, &b_full[s]);
         }
       }
     }
@@ -573,7 +587,7 @@ __global__ void __launch_bounds__(FH_THREADS, 1) forward_h_kernel(FwdHArgs a) {
 #pragma unroll
       for (int u = 0; u < KPT / 4; ++u) {
         e.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live && j < ntiles && KPT * j + 4 * u < Ds) e.v[u] = __ldg(reinterpret_cast<const float4*>(a.e_far + tg * Ds + KPT * j + 4 * u));
+        if (live && j < ntiles && KPT * (j0 + j) + 4 * u < Ds) e.v[u] = __ldg(reinterpret_cast<const float4*>(a.e_far + tg * Ds + KPT * (j0 + j) + 4 * u));
       }
       return e;
     };
@@ -600,10 +614,43 @@ __global__ void __launch_bounds__(FH_THREADS, 1) forward_h_kernel(FwdHArgs a) {
       for (int l = 0; l < L; ++l) xch[row * L + l] = facc[l];
     }
     asm volatile("bar.sync 2, 256;" ::: "memory");
-    if (half == 0 && live) {
+    if (half == 0) {
       const int ex = rexp[row] + bond_exponent(a.maxbits);
+      if (!partial) {
+        if (live) {
 #pragma unroll
-      for (int l = 0; l < L; ++l) a.f[tg * L + l] = scale_pow2(facc[l] + xch[row * L + l], ex);
+          for (int l = 0; l < L; ++l) a.f[tg * L + l] = scale_pow2(facc[l] + xch[row * L + l], ex);
+        }
+      } else {
+        const int rloc = rt - a.n_full;
+        float* mine = a.pscr + ((size_t)(rloc * a.parts + part) * FT_TM + row) * L;
+        if (live) {
+#pragma unroll
+          for (int l = 0; l < L; ++l) __stcg(&mine[l], scale_pow2(facc[l] + xch[row * L + l], ex));
+        }
+        __threadfence();
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+        if (tid == 0) {
+          const int old = atomicAdd(&a.pcnt[rloc], 1);
+          const int last = old == a.parts - 1;
+          if (last) a.pcnt[rloc] = 0;               // ready for the next launch
+          *s_last = last;
+        }
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+        if (*s_last && live) {
+          __threadfence();
+          float sum[L];
+#pragma unroll
+          for (int l = 0; l < L; ++l) sum[l] = 0.f;
+          for (int pq = 0; pq < a.parts; ++pq) {           // fixed order, whoever arrives last
+            const float* src = a.pscr + ((size_t)(rloc * a.parts + pq) * FT_TM + row) * L;
+#pragma unroll
+            for (int l = 0; l < L; ++l) sum[l] += __ldcg(&src[l]);
+          }
+#pragma unroll
+          for (int l = 0; l < L; ++l) a.f[tg * L + l] = sum[l];
+        }
+      }
     }
   }
   tc_fence_before();
@@ -624,7 +671,29 @@ bool forward_tc_supported(int Ds, int L, int nd) { return nd == 2 && L == 10 && 
 // floats needed for the hi/lo B images of one bond
 int64_t forward_tc_image_floats(int Ds, int L) {
   const int64_t ntiles = (Ds + 3) / 4, nchunks = (Ds + FT_KCH - 1) / FT_KCH;
-  return ntiles * nchunks * 2 * 16 * 16 * L + 64;      // the fp16 images need half of this; + the bond exponent word
+  return ntiles * nchunks * 2 * 16 * 16 * L + 64 + FH_PCNT + (int64_t)FH_PARTS_MAX * FH_TAIL_MAX * FT_TM * L;
+  // (the fp16 images need half of the first term; + the bond exponent word, the arrival counters and the partial logits of
+  //  the column-split tail tiles)
+}
+
+// how the image tiles of a launch are spread over the SMs: full waves of whole tiles, then the remaining `rem` tiles split
+// by columns over parts = floor(sms / rem) CTAs each (at most FH_PARTS_MAX and one column tile per CTA)
+static void forward_h_tail(int64_t B, int ntiles_cols, FwdHArgs& h, unsigned& grid, uint8_t* img_end) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  if (sms > FH_TAIL_MAX) sms = FH_TAIL_MAX;
+  const int64_t rtiles = ceil_div64(B, FT_TM);
+  const int rem = (int)(rtiles % sms);
+  int parts = rem > 0 ? sms / rem : 1;
+  if (parts > FH_PARTS_MAX) parts = FH_PARTS_MAX;
+  if (parts > ntiles_cols) parts = ntiles_cols;
+  if (parts < 1) parts = 1;
+  h.n_full = (int)(rtiles - rem);
+  h.parts = parts;
+  h.tpp = (ntiles_cols + parts - 1) / parts;
+  h.pcnt = reinterpret_cast<int32_t*>(img_end) + 16;                 // right behind the bond exponent word (cleared with it)
+  h.pscr = reinterpret_cast<float*>(img_end) + 16 + FH_PCNT;
+  grid = (unsigned)(h.n_full + (int64_t)rem * parts);
 }
 
 int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_near, const float* phi_far, const float* M,
@@ -640,7 +709,7 @@ int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_
     const int ntiles = (Ds + 3) / 4, nchunks = (Ds + FH_KCH - 1) / FH_KCH;
     uint8_t* img = reinterpret_cast<uint8_t*>(bimg);
     int32_t* maxbits = reinterpret_cast<int32_t*>(img + (size_t)ntiles * nchunks * 2 * 16 * L * 128);
-    TRMPS_CUDA_OK(cudaMemsetAsync(maxbits, 0, sizeof(int32_t), st));
+    TRMPS_CUDA_OK(cudaMemsetAsync(maxbits, 0, sizeof(int32_t) * (16 + FH_PCNT), st));
     absmax_kernel<<<148, 256, 0, st>>>(M, (int64_t)2 * Ds * 2 * L * Ds, maxbits);
     TRMPS_LAUNCH_OK("absmax_kernel");
     forward_prep_h_kernel<10><<<592, 256, 0, st>>>(M, img, maxbits, Ds, ntiles, nchunks);
@@ -654,7 +723,9 @@ int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_
       TRMPS_CUDA_OK(cudaFuncSetAttribute(forward_h_kernel<10, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
       attr_h = true;
     }
-    forward_h_kernel<10, 2><<<(unsigned)ceil_div64(B, FT_TM), FH_THREADS, smem_h, st>>>(h);
+    unsigned grid = 0;
+    forward_h_tail(B, ntiles, h, grid, reinterpret_cast<uint8_t*>(maxbits));
+    forward_h_kernel<10, 2><<<grid, FH_THREADS, smem_h, st>>>(h);
     TRMPS_LAUNCH_OK("forward_h_kernel");
     return TRMPS_OK;
   }
@@ -689,7 +760,7 @@ int launch_forward_site_tc(const float* e_near, const float* e_far, const float*
   const int ntiles = (Ds + 7) / 8, nchunks = (Ds + FH_KCH - 1) / FH_KCH;
   uint8_t* img = reinterpret_cast<uint8_t*>(bimg);
   int32_t* maxbits = reinterpret_cast<int32_t*>(img + (size_t)ntiles * nchunks * 2 * 16 * L * 128);
-  TRMPS_CUDA_OK(cudaMemsetAsync(maxbits, 0, sizeof(int32_t), st));
+  TRMPS_CUDA_OK(cudaMemsetAsync(maxbits, 0, sizeof(int32_t) * (16 + FH_PCNT), st));
   absmax_kernel<<<148, 256, 0, st>>>(special, (int64_t)2 * L * Ds * Ds, maxbits);
   TRMPS_LAUNCH_OK("absmax_kernel");
   forward_prep_site_kernel<10><<<296, 256, 0, st>>>(special, img, maxbits, Ds, dir, ntiles, nchunks);
@@ -703,7 +774,9 @@ int launch_forward_site_tc(const float* e_near, const float* e_far, const float*
     TRMPS_CUDA_OK(cudaFuncSetAttribute(forward_h_kernel<10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
     attr_h = true;
   }
-  forward_h_kernel<10, 1><<<(unsigned)ceil_div64(B, FT_TM), FH_THREADS, smem_h, st>>>(h);
+  unsigned grid = 0;
+  forward_h_tail(B, ntiles, h, grid, reinterpret_cast<uint8_t*>(maxbits));
+  forward_h_kernel<10, 1><<<grid, FH_THREADS, smem_h, st>>>(h);
   TRMPS_LAUNCH_OK("forward_h_kernel");
   return TRMPS_OK;
 }
