@@ -88,6 +88,7 @@ enum {
   TRMPS_I_N_SWEEPS = 7,   /* running count: Jacobi sweeps over all splits */
   TRMPS_I_SVD_ROT = 8,    /* [8 .. 8+64): per-sweep rotation counters of the running SVD */
   TRMPS_I_BARRIER = 80,   /* [80 .. 84): grid-barrier words of the SVD kernel */
+  TRMPS_I_ARRIVE = 84,    /* [84 .. 88): self-resetting arrival counters of the kernels whose last CTA finishes a reduction */
   TRMPS_I_COUNT = 96
 };
 
@@ -152,8 +153,8 @@ typedef struct {
   int32_t* dims;             /* N+1 */
   float*   envL;             /* N*B*Ds   C1s */
   float*   envR;             /* N*B*Ds   C2s */
-  float*   work;             /* layout.total floats */
-  int32_t* iwork;            /* TRMPS_I_COUNT ints */
+  float*   work;             /* layout.total floats, ZERO-INITIALISED by the caller once (self-resetting arrival counters live in it) */
+  int32_t* iwork;            /* TRMPS_I_COUNT ints, zero-initialised once */
   void*    comm;             /* trmps_comm* or NULL when world == 1 */
   int64_t  work_floats;      /* floats allocated behind `work`; every call checks it against the layout it computes */
 } trmps_sweep;

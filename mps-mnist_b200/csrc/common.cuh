@@ -140,20 +140,25 @@ int launch_special_to_matrix(const float* special, float* M, int Ds, int L, cuda
 int launch_sum_round_logits(const float* fpart, int nsplit, int64_t B, int L, int round_output, float* logits, cudaStream_t st);
 
 int launch_phi_site(const float* feat_site, int fm, int64_t B, float* out, cudaStream_t st);
+int launch_phi_pair(const float* feat_a, const float* feat_b, int fm, int64_t B, float* out_a, float* out_b, cudaStream_t st);
 
 struct LossArgs {
   const float* fpart; int nsplit; float* f0; const float* labels; const float* phi_far;
   float* resid; float* sres; float* hres; float* red; int64_t B; int L; int loss_kind; int from_parts;
+  int32_t* arrive; float* cost_sum; int32_t* clear_word;     // last-CTA reduction: arrival counter, un-normalised cost sum; a word to zero (or null)
 };
 struct ArmijoArgs {
   const float* f0; const float* fdpart; int nsplit; float* fd; const float* labels; float* red;
   int64_t B; int L; int loss_kind; float lr;
+  int32_t* arrive; float* trial; float trial_scale;          // last-CTA reduction: the 19 trial costs * trial_scale -> trial[]
+  int decide; float* scal; int32_t* iscal; float armijo_coeff;   // decide != 0: the accept / revert decision in the same launch (single rank)
 };
 int launch_loss(const LossArgs& a, cudaStream_t st);
 int launch_armijo(const ArmijoArgs& a, cudaStream_t st);
 int launch_sum_red(const float* red, int nrows, int ncols, float scale, float* dst, cudaStream_t st);
-int launch_grad_finish(float* G, const float* M, const float* H, float* delta, int64_t n, float reg, float hess_add,
-                       float* red, int nblocks, cudaStream_t st);
+int launch_grad_finish(float* G, const float* M, const float* H, float* delta, const float* parts, int nparts, int64_t n, float reg,
+                       float hess_add, float gdc_scale, const float* cost_sum, float cost_scale, float* red, float* scal,
+                       int32_t* arrive, int32_t* maxbits, int nblocks, cudaStream_t st);
 int launch_decide(float* scal, const float* trial, int32_t* iscal, float lr, float coeff, cudaStream_t st);
 int launch_apply_update(float* M, const float* delta, int64_t n, float* f0, const float* fd, int64_t nf, const float* scal,
                         cudaStream_t st);
@@ -180,7 +185,8 @@ bool forward_tc_supported(int Ds, int L, int nd);
 int64_t forward_tc_image_floats(int Ds, int L);
 int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_near, const float* phi_far, const float* M,
                       float* bimg, float* f_out, int64_t B, int Ds, int L, const int32_t* d_near, const int32_t* d_far,
-                      cudaStream_t st);
+                      cudaStream_t st, bool have_max = false);
+int32_t* forward_tc_maxbits(float* bimg, int Ds, int L);
 bool forward_site_tc_supported(int Ds, int L);
 int launch_forward_site_tc(const float* e_near, const float* e_far, const float* phi_near, const float* special, int dir, float* bimg,
                            float* f_out, int64_t B, int Ds, int L, const int32_t* d_near, const int32_t* d_far, cudaStream_t st);

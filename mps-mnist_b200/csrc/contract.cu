@@ -309,6 +309,42 @@ int launch_grad(const float* e_near, const float* e_far, const float* phi_near, 
   return TRMPS_OK;
 }
 
+// Fixed-order sum of the per-CTA partials red[r][c] (r < nrows, c < ncols <= 32) by ONE CTA of >= 256 threads: 8 row groups
+// per pass over 32 groups (rows r = g, g + 32, ..), then the groups in order -- the summation order of sum_red_kernel, so a
+// kernel whose last CTA to arrive finishes its own reduction gives the same bits as the two-launch form.
+__device__ __forceinline__ void fixed_order_reduce(const float* __restrict__ red, int nrows, int ncols, float* part /* [32][33] shared */) {
+  const int c = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int g = w; g < 32; g += nw) {
+    float s = 0.f;
+    if (c < ncols)
+      for (int r = g; r < nrows; r += 32) s += __ldcg(&red[r * 32 + c]);
+    part[g * 33 + c] = s;
+  }
+  __syncthreads();
+  if (w == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += part[k * 33 + c];
+    part[c] = t;                 // row 0 is only read by this lane's own column
+  }
+  __syncthreads();
+}
+// arrival of this CTA at a self-resetting counter; true in every thread of the last CTA to arrive
+__device__ __forceinline__ bool last_cta_arrives(int32_t* counter, int* s_flag) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(counter, 1);
+    const int last = old == (int)gridDim.x - 1;
+    if (last) *counter = 0;
+    *s_flag = last;
+  }
+  __syncthreads();
+  const bool last = *s_flag != 0;
+  if (last) __threadfence();
+  return last;
+}
+
 // out[i] = sum_s part[s][i]   (fixed order -> bit-reproducible)
 __global__ void sum_parts_kernel(const float4* __restrict__ part, int nparts, int64_t n4, float4* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -329,24 +365,57 @@ int launch_sum_parts(const float* part, int nparts, int64_t n, float* out, cudaS
   return TRMPS_OK;
 }
 
-// G -= 2*reg*M ; delta = G / H (Hessian on) ; per-CTA partial of <G, delta>       optimizer.py:249-253
-__global__ void grad_finish_kernel(float* __restrict__ G, const float* __restrict__ M, const float* __restrict__ H,
-                                   float* __restrict__ delta, int64_t n, float reg, float hess_add, float* __restrict__ red) {
+// G (= sum of the split-K parts when `parts` is given, in a fixed order) -= 2*reg*M ; delta = G / H (Hessian on) ;
+// <G, delta> / B_total -> scal[S_GDC] by the last CTA to arrive (fixed-order sum of the per-CTA partials) ;
+// scal[S_COST0] = cost sum * cost_scale ; largest |delta| -> *maxbits (integer atomicMax: order independent), the exponent
+// the next forward contraction scales delta by                                                     optimizer.py:249-253
+struct GradFinishArgs {
+  float* G; const float* M; const float* H; float* delta; const float* parts; int nparts; int64_t n;
+  float reg, hess_add, gdc_scale, cost_scale; const float* cost_sum; float* red; float* scal; int32_t* arrive; int32_t* maxbits;
+};
+__global__ void __launch_bounds__(256) grad_finish_kernel(GradFinishArgs a) {
   __shared__ float sred[32];
-  float local = 0.f;
-  const float two_reg = 2.f * reg;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float gv = G[i] - two_reg * M[i];
-    G[i] = gv;
-    float dv = gv;
-    if (H) {
-      dv = gv / (H[i] + hess_add);
-      delta[i] = dv;
+  __shared__ float part[32 * 33];
+  __shared__ int s_flag;
+  float local = 0.f, amax = 0.f;
+  const float two_reg = 2.f * a.reg;
+  const int64_t n4 = a.n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 g;
+    if (a.parts) {
+      g = __ldcs(reinterpret_cast<const float4*>(a.parts) + i);
+      for (int p = 1; p < a.nparts; ++p) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(a.parts) + (int64_t)p * n4 + i);
+        g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+      }
+    } else {
+      g = reinterpret_cast<const float4*>(a.G)[i];
     }
-    local = fmaf(gv, dv, local);
+    const float4 m = reinterpret_cast<const float4*>(a.M)[i];
+    g.x -= two_reg * m.x; g.y -= two_reg * m.y; g.z -= two_reg * m.z; g.w -= two_reg * m.w;
+    reinterpret_cast<float4*>(a.G)[i] = g;
+    float4 d = g;
+    if (a.H) {
+      const float4 h = reinterpret_cast<const float4*>(a.H)[i];
+      d.x = g.x / (h.x + a.hess_add); d.y = g.y / (h.y + a.hess_add); d.z = g.z / (h.z + a.hess_add); d.w = g.w / (h.w + a.hess_add);
+      reinterpret_cast<float4*>(a.delta)[i] = d;
+    }
+    local = fmaf(g.x, d.x, local); local = fmaf(g.y, d.y, local); local = fmaf(g.z, d.z, local); local = fmaf(g.w, d.w, local);
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
   }
-  float s = block_sum(local, sred);
-  if (threadIdx.x == 0) red[blockIdx.x * 32] = s;
+  if (a.maxbits) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(a.maxbits, __float_as_int(amax));
+  }
+  const float s = block_sum(local, sred);
+  if (threadIdx.x == 0) __stcg(&a.red[blockIdx.x * 32], s);
+  if (!last_cta_arrives(a.arrive, &s_flag)) return;
+  fixed_order_reduce(a.red, (int)gridDim.x, 1, part);
+  if (threadIdx.x == 0) {
+    a.scal[TRMPS_S_GDC] = part[0] * a.gdc_scale;
+    a.scal[TRMPS_S_COST0] = __ldcg(a.cost_sum) * a.cost_scale;
+  }
 }
 
 // dst[c] = scale * sum_r red[r][c]  for c < ncols <= 32: 32 row groups sum their rows (r = g, g + 32, ..) in order, then the groups
@@ -432,7 +501,41 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
     }
   }
   float s = block_sum(cost_t, sred);
-  if (threadIdx.x == 0) a.red[blockIdx.x * 32] = s;
+  if (threadIdx.x == 0) __stcg(&a.red[blockIdx.x * 32], s);
+  // the last CTA to arrive adds the per-CTA sums in a fixed order (one launch instead of loss + sum_red)
+  __shared__ float part[32 * 33];
+  __shared__ int s_flag;
+  if (!last_cta_arrives(a.arrive, &s_flag)) return;
+  fixed_order_reduce(a.red, (int)gridDim.x, 1, part);
+  if (threadIdx.x == 0) {
+    *a.cost_sum = part[0];
+    if (a.clear_word) *a.clear_word = 0;          // the atomicMax word grad_finish_kernel fills
+  }
+}
+
+// single-thread decision: Armijo acceptance + accept-only-if-cost-dropped     baseoptimizer.py:299-322, optimizer.py:257-262
+__device__ __forceinline__ void decide_update(float* __restrict__ scal, const float* __restrict__ trial, int32_t* __restrict__ iscal,
+                                              float lr, float armijo_coeff) {
+  const float cost0 = scal[TRMPS_S_COST0], gdc = scal[TRMPS_S_GDC];
+  float lr_c = lr, lr_star = 0.f, cost1 = cost0;
+  int trials = 0;
+  bool found = false;
+  for (int c = 0; c < 19; ++c) {
+    ++trials;
+    float cost_c = trial[c];
+    float target = cost0 - armijo_coeff * lr_c * gdc;
+    if (!(cost_c > target)) { found = true; lr_star = lr_c; cost1 = cost_c; break; }
+    lr_c *= 0.5f;
+  }
+  bool accept = found && (cost1 < cost0);
+  if (!found) iscal[TRMPS_I_N_EXHAUST] += 1;
+  if (!accept) { lr_star = 0.f; iscal[TRMPS_I_N_REVERT] += 1; }
+  iscal[TRMPS_I_N_UPDATES] += 1;
+  iscal[TRMPS_I_ACCEPT] = accept ? 1 : 0;
+  iscal[TRMPS_I_TRIALS] = trials;
+  scal[TRMPS_S_LR_STAR] = lr_star;
+  scal[TRMPS_S_COST1] = accept ? cost1 : cost0;
+  scal[TRMPS_S_LR] = lr;
 }
 
 // Armijo trial costs for lr, lr/2, ... (19 values) from f0 and fd = f(delta)      baseoptimizer.py:299-322
@@ -484,34 +587,24 @@ __global__ void __launch_bounds__(256) armijo_kernel(ArmijoArgs a) {
   if (threadIdx.x < 19) {
     float s = 0.f;
     for (int i = 0; i < 8; ++i) s += swarp[i][threadIdx.x];
-    a.red[blockIdx.x * 32 + threadIdx.x] = s;
+    __stcg(&a.red[blockIdx.x * 32 + threadIdx.x], s);
+  }
+  // the last CTA to arrive: the 19 trial sums in a fixed order and, on a single rank, the decision itself
+  __shared__ float part[32 * 33];
+  __shared__ int s_flag;
+  if (!last_cta_arrives(a.arrive, &s_flag)) return;
+  fixed_order_reduce(a.red, (int)gridDim.x, 19, part);
+  if (threadIdx.x < 19) a.trial[threadIdx.x] = part[threadIdx.x] * a.trial_scale;
+  if (a.decide) {
+    __syncthreads();
+    if (threadIdx.x == 0) decide_update(a.scal, a.trial, a.iscal, a.lr, a.armijo_coeff);
   }
 }
 
-// single-thread decision: Armijo acceptance + accept-only-if-cost-dropped     baseoptimizer.py:299-322, optimizer.py:257-262
 __global__ void decide_kernel(float* __restrict__ scal, const float* __restrict__ trial, int32_t* __restrict__ iscal,
                               float lr, float armijo_coeff) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const float cost0 = scal[TRMPS_S_COST0], gdc = scal[TRMPS_S_GDC];
-  float lr_c = lr, lr_star = 0.f, cost1 = cost0;
-  int trials = 0;
-  bool found = false;
-  for (int c = 0; c < 19; ++c) {
-    ++trials;
-    float cost_c = trial[c];
-    float target = cost0 - armijo_coeff * lr_c * gdc;
-    if (!(cost_c > target)) { found = true; lr_star = lr_c; cost1 = cost_c; break; }
-    lr_c *= 0.5f;
-  }
-  bool accept = found && (cost1 < cost0);
-  if (!found) iscal[TRMPS_I_N_EXHAUST] += 1;
-  if (!accept) { lr_star = 0.f; iscal[TRMPS_I_N_REVERT] += 1; }
-  iscal[TRMPS_I_N_UPDATES] += 1;
-  iscal[TRMPS_I_ACCEPT] = accept ? 1 : 0;
-  iscal[TRMPS_I_TRIALS] = trials;
-  scal[TRMPS_S_LR_STAR] = lr_star;
-  scal[TRMPS_S_COST1] = accept ? cost1 : cost0;
-  scal[TRMPS_S_LR] = lr;
+  decide_update(scal, trial, iscal, lr, armijo_coeff);
 }
 
 // M += lr* delta ; f0 += lr* fd
@@ -614,9 +707,13 @@ int launch_sum_red(const float* red, int nrows, int ncols, float scale, float* d
   TRMPS_LAUNCH_OK("sum_red_kernel");
   return TRMPS_OK;
 }
-int launch_grad_finish(float* G, const float* M, const float* H, float* delta, int64_t n, float reg, float hess_add,
-                       float* red, int nblocks, cudaStream_t st) {
-  grad_finish_kernel<<<nblocks, 256, 0, st>>>(G, M, H, delta, n, reg, hess_add, red);
+int launch_grad_finish(float* G, const float* M, const float* H, float* delta, const float* parts, int nparts, int64_t n, float reg,
+                       float hess_add, float gdc_scale, const float* cost_sum, float cost_scale, float* red, float* scal,
+                       int32_t* arrive, int32_t* maxbits, int nblocks, cudaStream_t st) {
+  GradFinishArgs a;
+  a.G = G; a.M = M; a.H = H; a.delta = delta; a.parts = parts; a.nparts = nparts; a.n = n; a.reg = reg; a.hess_add = hess_add;
+  a.gdc_scale = gdc_scale; a.cost_scale = cost_scale; a.cost_sum = cost_sum; a.red = red; a.scal = scal; a.arrive = arrive; a.maxbits = maxbits;
+  grad_finish_kernel<<<nblocks, 256, 0, st>>>(a);
   TRMPS_LAUNCH_OK("grad_finish_kernel");
   return TRMPS_OK;
 }

@@ -309,6 +309,20 @@ __global__ void phi_site_kernel(const float* __restrict__ feat_site, int fm, int
   if (t < B) out[t] = load_phi(feat_site, fm, t);
 }
 
+// the feature vectors of both sites of a bond in one launch
+__global__ void phi_pair_kernel(const float* __restrict__ feat_a, const float* __restrict__ feat_b, int fm, int64_t B,
+                                float2* __restrict__ out_a, float2* __restrict__ out_b) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < B) { out_a[t] = load_phi(feat_a, fm, t); out_b[t] = load_phi(feat_b, fm, t); }
+}
+
+int launch_phi_pair(const float* feat_a, const float* feat_b, int fm, int64_t B, float* out_a, float* out_b, cudaStream_t st) {
+  if (B == 0) return TRMPS_OK;
+  phi_pair_kernel<<<(unsigned)ceil_div64(B, 256), 256, 0, st>>>(feat_a, feat_b, fm, B, reinterpret_cast<float2*>(out_a), reinterpret_cast<float2*>(out_b));
+  TRMPS_LAUNCH_OK("phi_pair_kernel");
+  return TRMPS_OK;
+}
+
 int launch_phi_site(const float* feat_site, int fm, int64_t B, float* out, cudaStream_t st) {
   if (B == 0) return TRMPS_OK;
   phi_site_kernel<<<(unsigned)ceil_div64(B, 256), 256, 0, st>>>(feat_site, fm, B, reinterpret_cast<float2*>(out));

@@ -696,9 +696,17 @@ static void forward_h_tail(int64_t B, int ntiles_cols, FwdHArgs& h, unsigned& gr
   grid = (unsigned)(h.n_full + (int64_t)rem * parts);
 }
 
+// where the fp16 forward keeps the bits of the largest |bond entry| (two-site form): a kernel that produces the bond may fill
+// it with an integer atomicMax and pass have_max = true to launch_forward_tc (null when the fp16 forward is not in use)
+int32_t* forward_tc_maxbits(float* bimg, int Ds, int L) {
+  if (option_value(1) != 0 || !forward_tc_supported(Ds, L, 2)) return nullptr;
+  const int ntiles = (Ds + 3) / 4, nchunks = (Ds + FH_KCH - 1) / FH_KCH;
+  return reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(bimg) + (size_t)ntiles * nchunks * 2 * 16 * L * 128);
+}
+
 int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_near, const float* phi_far, const float* M,
                       float* bimg, float* f_out, int64_t B, int Ds, int L, const int32_t* d_near, const int32_t* d_far,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool have_max) {
   if (B <= 0) return TRMPS_OK;
   if (!forward_tc_supported(Ds, L, 2)) {
     set_error("forward_tc: unsupported shape Ds=%d L=%d", Ds, L);
@@ -709,9 +717,11 @@ int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_
     const int ntiles = (Ds + 3) / 4, nchunks = (Ds + FH_KCH - 1) / FH_KCH;
     uint8_t* img = reinterpret_cast<uint8_t*>(bimg);
     int32_t* maxbits = reinterpret_cast<int32_t*>(img + (size_t)ntiles * nchunks * 2 * 16 * L * 128);
-    TRMPS_CUDA_OK(cudaMemsetAsync(maxbits, 0, sizeof(int32_t) * (16 + FH_PCNT), st));
-    absmax_kernel<<<148, 256, 0, st>>>(M, (int64_t)2 * Ds * 2 * L * Ds, maxbits);
-    TRMPS_LAUNCH_OK("absmax_kernel");
+    if (!have_max) {
+      TRMPS_CUDA_OK(cudaMemsetAsync(maxbits, 0, sizeof(int32_t) * (16 + FH_PCNT), st));
+      absmax_kernel<<<148, 256, 0, st>>>(M, (int64_t)2 * Ds * 2 * L * Ds, maxbits);
+      TRMPS_LAUNCH_OK("absmax_kernel");
+    }
     forward_prep_h_kernel<10><<<592, 256, 0, st>>>(M, img, maxbits, Ds, ntiles, nchunks);
     TRMPS_LAUNCH_OK("forward_prep_h_kernel");
     FwdHArgs h;
@@ -760,7 +770,7 @@ int launch_forward_site_tc(const float* e_near, const float* e_far, const float*
   const int ntiles = (Ds + 7) / 8, nchunks = (Ds + FH_KCH - 1) / FH_KCH;
   uint8_t* img = reinterpret_cast<uint8_t*>(bimg);
   int32_t* maxbits = reinterpret_cast<int32_t*>(img + (size_t)ntiles * nchunks * 2 * 16 * L * 128);
-  TRMPS_CUDA_OK(cudaMemsetAsync(maxbits, 0, sizeof(int32_t) * (16 + FH_PCNT), st));
+  TRMPS_CUDA_OK(cudaMemsetAsync(maxbits, 0, sizeof(int32_t), st));
   absmax_kernel<<<148, 256, 0, st>>>(special, (int64_t)2 * L * Ds * Ds, maxbits);
   TRMPS_LAUNCH_OK("absmax_kernel");
   forward_prep_site_kernel<10><<<296, 256, 0, st>>>(special, img, maxbits, Ds, dir, ntiles, nchunks);
@@ -775,7 +785,8 @@ int launch_forward_site_tc(const float* e_near, const float* e_far, const float*
     attr_h = true;
   }
   unsigned grid = 0;
-  forward_h_tail(B, ntiles, h, grid, reinterpret_cast<uint8_t*>(maxbits));
+  // (the arrival counters and the partial logits of the tail tiles sit behind the TWO-site image, whichever form runs)
+  forward_h_tail(B, ntiles, h, grid, img + (size_t)((Ds + 3) / 4) * nchunks * 2 * 16 * L * 128);
   forward_h_kernel<10, 1><<<grid, FH_THREADS, smem_h, st>>>(h);
   TRMPS_LAUNCH_OK("forward_h_kernel");
   return TRMPS_OK;

@@ -211,9 +211,8 @@ static BondGeom site_geom(const trmps_sweep* s, int site, int dir) {
 
 static int phi_pair(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, cudaStream_t st) {
   float* phi2 = s->work + lay.phi2;
-  int rc = launch_phi_site(s->feat + feat_site_offset(s->feature_map, s->B, g.near_site), s->feature_map, s->B, phi2, st);
-  if (rc) return rc;
-  return launch_phi_site(s->feat + feat_site_offset(s->feature_map, s->B, g.far_site), s->feature_map, s->B, phi2 + 2 * s->B, st);
+  return launch_phi_pair(s->feat + feat_site_offset(s->feature_map, s->B, g.near_site),
+                         s->feat + feat_site_offset(s->feature_map, s->B, g.far_site), s->feature_map, s->B, phi2, phi2 + 2 * s->B, st);
 }
 
 static int do_merge(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, cudaStream_t st) {
@@ -222,12 +221,13 @@ static int do_merge(const trmps_sweep* s, const trmps_layout& lay, const BondGeo
                       g.d_mid, st);
 }
 
-static int do_forward(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const float* M, cudaStream_t st) {
+static int do_forward(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const float* M, cudaStream_t st,
+                      bool have_max = false) {
   ProfScope ps(PROF_FORWARD, st);
   const float* phi2 = s->work + lay.phi2;
   if (g_fwd_impl != 1 && forward_tc_supported(s->Ds, s->L, 2))
     return launch_forward_tc(g.e_near, g.e_far, phi2, phi2 + 2 * s->B, M, s->work + lay.bimg, s->work + lay.fpart, s->B, s->Ds,
-                             s->L, g.d_near, g.d_far, st);
+                             s->L, g.d_near, g.d_far, st, have_max);
   return launch_forward(g.e_near, g.e_far, phi2, phi2 + 2 * s->B, M, s->work + lay.fpart, lay.nsplit, s->B, s->Ds, s->L, 2,
                         g.d_near, st);
 }
@@ -238,7 +238,7 @@ static float cost_norm(const trmps_sweep* s) {
 
 // loss + gradient (+Hessian) + all-reduce + finish; leaves G in gradM, delta in deltaM (Hessian) or gradM
 static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, const trmps_opt* opt, int from_parts,
-                       cudaStream_t st) {
+                       cudaStream_t st, int32_t* delta_maxbits) {
   static const bool grad_debug = getenv("TRMPS_GRAD_DEBUG") != nullptr;      // development: phase timers of grad_tc in hres
   const int Ds = s->Ds, L = s->L;
   const int64_t RC = (int64_t)2 * Ds * 2 * L * Ds;
@@ -250,13 +250,16 @@ static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const Bond
   la.hres = hess ? w + lay.hres : nullptr; la.red = w + lay.red; la.B = s->B; la.L = L; la.loss_kind = s->loss_kind;
   la.from_parts = from_parts;
   int rc;
-  const int nblk = (int)ceil_div64(s->B, 256);
   float* tail = w + lay.gradM + RC;
+  // the un-normalised cost sum goes behind the gradient (one all-reduce carries both); the last CTA of the loss kernel writes it
+  la.arrive = s->iwork + TRMPS_I_ARRIVE; la.cost_sum = tail; la.clear_word = delta_maxbits;
   {
     ProfScope ps(PROF_SCALAR, st);
     if ((rc = launch_loss(la, st))) return rc;
-    if ((rc = launch_sum_red(w + lay.red, nblk, 1, 1.0f, tail, st))) return rc;
   }
+  const bool one_rank = s->comm == nullptr && !hess;      // (the Hessian pass reuses the split-K buffer: sum the gradient's parts first)
+  const float* parts = nullptr;             // single rank: the split-K parts are summed by grad_finish_kernel itself
+  int nparts = 0;
   {
     ProfScope ps(PROF_GRAD, st);
     if (g_grad_impl == 2 && grad_h_supported(s->B, Ds, L)) {
@@ -267,10 +270,12 @@ static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const Bond
         return rc;
     } else if (g_grad_impl != 1) {
       if ((rc = launch_grad_tc(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit_tc, s->B, Ds, L, st, grad_debug ? w + lay.hres : nullptr))) return rc;
-      if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit_tc, RC, w + lay.gradM, st))) return rc;
+      if (one_rank) { parts = w + lay.gpart; nparts = lay.gsplit_tc; }
+      else if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit_tc, RC, w + lay.gradM, st))) return rc;
     } else {
       if ((rc = launch_grad(g.e_near, g.e_far, w + lay.phi2, w + lay.sres, w + lay.gpart, lay.gsplit, s->B, Ds, L, false, st))) return rc;
-      if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit, RC, w + lay.gradM, st))) return rc;
+      if (one_rank) { parts = w + lay.gpart; nparts = lay.gsplit; }
+      else if ((rc = launch_sum_parts(w + lay.gpart, lay.gsplit, RC, w + lay.gradM, st))) return rc;
     }
   }
   {
@@ -291,11 +296,10 @@ static int do_gradient(const trmps_sweep* s, const trmps_layout& lay, const Bond
   }
   float* scal = w + lay.scal;
   ProfScope ps(PROF_SCALAR, st);
-  if ((rc = launch_sum_red(tail, 1, 1, cost_norm(s), scal + TRMPS_S_COST0, st))) return rc;
-  if ((rc = launch_grad_finish(w + lay.gradM, w + lay.bondM, hess ? w + lay.hessM : nullptr, w + lay.deltaM, RC, opt->reg,
-                               2.f * opt->reg, w + lay.red, 296, st)))
-    return rc;
-  return launch_sum_red(w + lay.red, 296, 1, 1.0f / (float)s->B_total, scal + TRMPS_S_GDC, st);
+  // regulariser, delta, <G, delta> / B, the normalised cost and the exponent of delta for the next forward: one launch
+  return launch_grad_finish(w + lay.gradM, w + lay.bondM, hess ? w + lay.hessM : nullptr, w + lay.deltaM, parts, nparts, RC, opt->reg,
+                            2.f * opt->reg, 1.0f / (float)s->B_total, tail, cost_norm(s), w + lay.red, scal,
+                            s->iwork + TRMPS_I_ARRIVE + 1, delta_maxbits, 296, st);
 }
 
 // gradient step(s) with Armijo backtracking and accept/revert on the bond matrix in bondM (optimizer.py:239-264,
@@ -320,17 +324,23 @@ static int do_update_bond(const trmps_sweep* s, const trmps_layout& lay, const B
       return rc;
   } else if ((rc = do_forward(s, lay, g, w + lay.bondM, st))) return rc;
   const int nupd = opt->updates_per_step > 0 ? opt->updates_per_step : 0;
+  // the fp16 forward scales delta by one power of two: grad_finish_kernel finds it while it writes delta
+  int32_t* delta_maxbits = forward_tc_maxbits(w + lay.bimg, s->Ds, L);
   for (int u = 0; u < nupd; ++u) {                                  // baseoptimizer.py:324-332
-    if ((rc = do_gradient(s, lay, g, opt, u == 0, st))) return rc;
-    if ((rc = do_forward(s, lay, g, delta, st))) return rc;         // f(delta): serves every Armijo trial
+    if ((rc = do_gradient(s, lay, g, opt, u == 0, st, delta_maxbits))) return rc;
+    if ((rc = do_forward(s, lay, g, delta, st, delta_maxbits != nullptr))) return rc;         // f(delta): serves every Armijo trial
     ArmijoArgs aa;
     aa.f0 = w + lay.f0; aa.fdpart = w + lay.fpart; aa.nsplit = eff_nsplit(s, lay); aa.fd = w + lay.fd; aa.labels = s->labels;
     aa.red = w + lay.red; aa.B = s->B; aa.L = L; aa.loss_kind = s->loss_kind; aa.lr = opt->lr;
+    // the 19 trial sums by the kernel's last CTA; on a single rank the accept / revert decision too
+    aa.arrive = s->iwork + TRMPS_I_ARRIVE + 2; aa.trial = scal + 8; aa.trial_scale = cost_norm(s);
+    aa.decide = s->comm == nullptr; aa.scal = scal; aa.iscal = s->iwork; aa.armijo_coeff = opt->armijo_coeff;
     ProfScope ps(PROF_SCALAR, st);
     if ((rc = launch_armijo(aa, st))) return rc;
-    if ((rc = launch_sum_red(w + lay.red, (int)ceil_div64(s->B, 256), 19, cost_norm(s), scal + 8, st))) return rc;
-    if ((rc = allreduce_sum(s->comm, scal + 8, 20, st))) return rc;
-    if ((rc = launch_decide(scal, scal + 8, s->iwork, opt->lr, opt->armijo_coeff, st))) return rc;
+    if (!aa.decide) {
+      if ((rc = allreduce_sum(s->comm, scal + 8, 20, st))) return rc;
+      if ((rc = launch_decide(scal, scal + 8, s->iwork, opt->lr, opt->armijo_coeff, st))) return rc;
+    }
     if ((rc = launch_apply_update(w + lay.bondM, delta, RC, w + lay.f0, w + lay.fd, s->B * L, scal, st))) return rc;
   }
   return TRMPS_OK;
@@ -652,7 +662,7 @@ extern "C" int trmps_bond_gradient(const trmps_sweep* s, int32_t site, int32_t d
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = phi_pair(s, lay, g, st))) return rc;
   if ((rc = do_forward(s, lay, g, s->work + lay.bondM, st))) return rc;
-  return do_gradient(s, lay, g, opt, 1, st);
+  return do_gradient(s, lay, g, opt, 1, st, nullptr);
 }
 
 extern "C" int trmps_bond_split(const trmps_sweep* s, int32_t site, int32_t dir, const trmps_opt* opt, void* stream) {
