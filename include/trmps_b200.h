@@ -187,7 +187,10 @@ int         trmps_set_option(int32_t option, int32_t value); /* option 0: gradie
                                                             chain's rounding-bias estimate stays below 9e-5, 1 = FP32 SIMT steps;
                                                             option 5: first forward of a two-site update: 1 (default) = single-site form
                                                             (special node x cached environment of the same site, half the contraction; needs the
-                                                            environments trmps_sweep_init_env / the sweeps keep), 0 = on the merged bond */
+                                                            environments trmps_sweep_init_env / the sweeps keep), 0 = on the merged bond;
+                                                            option 6: fp16 forward contraction by CTA pairs (tcgen05 cta_group::2, each CTA holds half of
+                                                            every bond image; the peer's half is announced to the leader by a relayed mbarrier arrive): 0 (default) = one CTA per image
+                                                            tile, 1 = CTA pairs (parity-tested alternative: 0.180 against 0.165 ms per cfg3 launch) */
 int64_t     trmps_launch_count(void);                   /* kernels launched by this library so far (process-wide) */
 
 /* optional device-side timing of the kernels a sweep launches (CUDA events on the caller's stream; replaces the

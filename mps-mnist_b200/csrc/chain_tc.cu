@@ -293,8 +293,12 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
       }
     }
   } else if (warp == EPI_WARPS) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the schedule (uniform control flow and descriptor arithmetic stay in the uniform
+    //       datapath), one elected lane issues the MMAs and commits =====
+    {
+      uint32_t el_;
+      asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(el_));
+      const bool issuer = el_ != 0;
       // kind::f16: fp16 x fp16 -> fp32, both operands K-major, N = 2*KP, M = 128
       const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(CH_TM >> 4) << 24);
       const uint64_t adesc0 = make_desc_k128(smem_u32(a_base)), bdesc0 = make_desc_k128(smem_u32(n_base));
@@ -308,24 +312,24 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
         const uint64_t ad = adesc0 + (uint64_t)(k * (C::A_BYTES >> 4));
         const uint64_t bd = bdesc0 + (uint64_t)(st * (C::PIECE_BYTES >> 4));
         if (KP == 32) {                                    // small terms first (see "Order of accumulation")
-          umma_f16(d, ad + 4, bd + 0, idesc, 0u);          // lo . hi
-          umma_f16(d, ad + 6, bd + 2, idesc, 1u);
-          umma_f16(d, ad + 0, bd + 4, idesc, 1u);          // hi . lo
-          umma_f16(d, ad + 2, bd + 6, idesc, 1u);
-          umma_f16(d, ad + 0, bd + 0, idesc, 1u);          // hi . hi
-          umma_f16(d, ad + 2, bd + 2, idesc, 1u);
+          if (issuer) umma_f16(d, ad + 4, bd + 0, idesc, 0u);          // lo . hi
+          if (issuer) umma_f16(d, ad + 6, bd + 2, idesc, 1u);
+          if (issuer) umma_f16(d, ad + 0, bd + 4, idesc, 1u);          // hi . lo
+          if (issuer) umma_f16(d, ad + 2, bd + 6, idesc, 1u);
+          if (issuer) umma_f16(d, ad + 0, bd + 0, idesc, 1u);          // hi . hi
+          if (issuer) umma_f16(d, ad + 2, bd + 2, idesc, 1u);
         } else {
           constexpr int KA = KP / 64;
           const int ka = p < KA ? p : p - KA;
           const uint64_t ahi = ad + (uint64_t)(ka * 1024), alo = ad + (uint64_t)((KA + ka) * 1024);
           if (p < KA) {                                    // piece holds g_lo of atom ka: a_hi . g_lo
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_f16(d, ahi + 2 * ks, bd + 2 * ks, idesc, (p > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks) if (issuer) umma_f16(d, ahi + 2 * ks, bd + 2 * ks, idesc, (p > 0 || ks > 0) ? 1u : 0u);
           } else {                                         // piece holds g_hi of atom ka: a_lo . g_hi, then a_hi . g_hi
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_f16(d, alo + 2 * ks, bd + 2 * ks, idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks) if (issuer) umma_f16(d, alo + 2 * ks, bd + 2 * ks, idesc, 1u);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_f16(d, ahi + 2 * ks, bd + 2 * ks, idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks) if (issuer) umma_f16(d, ahi + 2 * ks, bd + 2 * ks, idesc, 1u);
           }
         }
       };
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
       };
       for (int s = 0; s < nsteps; ++s) {
         const bool ev = itimer && s == nsteps / 2;
-        if (ev) g_chain_dbg[16] = (float)(clock64() - t_base);
+        if (ev && issuer) g_chain_dbg[16] = (float)(clock64() - t_base);
         if (C::TILE_MAJOR) {
           // tile 0 waits for a piece, the last tile releases it
 #pragma unroll
@@ -347,11 +351,11 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
               const uint32_t q = (uint32_t)(s * PIECES + p), st = q % NSTAGE;
               if (k == 0) { mbar_wait(&node_full[st], (q / NSTAGE) & 1u); itick(0); }
               issue(k, p, st);
-              if (k == TILES - 1) umma_commit(&node_empty[st]);
+              if (k == TILES - 1) if (issuer) umma_commit(&node_empty[st]);
             }
-            umma_commit(&x_ready[k]);
+            if (issuer) umma_commit(&x_ready[k]);
             itick(2);
-            if (ev && k < 4) g_chain_dbg[17 + k] = (float)(clock64() - t_base);      // issued tile k
+            if (ev && issuer && k < 4) g_chain_dbg[17 + k] = (float)(clock64() - t_base);      // issued tile k
           }
         } else {
           // Two tiles sharing a 3-stage ring.  Tile 0 runs two pieces ahead of tile 1,
@@ -368,15 +372,15 @@ __global__ void __launch_bounds__(chain_threads<KP>(), 1) chain_tc_kernel(ChainA
             if (p == 0) wait_a(k, s);
             issue(k, p, st);
             if (p == PIECES - 1) {
-              umma_commit(&x_ready[k]);
-              if (ev) g_chain_dbg[17 + k] = (float)(clock64() - t_base);
+              if (issuer) umma_commit(&x_ready[k]);
+              if (ev && issuer) g_chain_dbg[17 + k] = (float)(clock64() - t_base);
             }
-            if (k == 1) umma_commit(&node_empty[st]);
+            if (k == 1) if (issuer) umma_commit(&node_empty[st]);
             itick(2);
           }
         }
       }
-      if (itimer) for (int q = 0; q < 3; ++q) g_chain_dbg[4 + q] = (float)iacc[q];
+      if (itimer && issuer) for (int q = 0; q < 3; ++q) g_chain_dbg[4 + q] = (float)iacc[q];
     }
   } else {
     // ===== epilogue: warpgroup g of tile k owns state columns [g*JW, (g+1)*JW) of every image row =====

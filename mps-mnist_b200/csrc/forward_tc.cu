@@ -363,6 +363,14 @@ struct FwdHArgs {
   int n_full, parts, tpp; float* pscr; int32_t* pcnt;
 };
 
+// one lane of a converged warp (the lowest): the MMA warp runs its loop as a whole -- uniform control flow and descriptor
+// arithmetic, which the compiler then keeps in the uniform datapath -- and this lane issues.  (A loop under `if (lane == 0)`
+// made every descriptor a per-thread value: ELECT + 3 R2UR.BROADCAST per MMA, 154 cycles between MMAs against 95 of execution.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 constexpr int FH_PARTS_MAX = 6, FH_TAIL_MAX = 160, FH_PCNT = 256;   // column parts per tail tile, SMs sized for, counter words
 constexpr int FH_THREADS = 320;        // warps 0-7: epilogue (TMEM lane quadrant x column half), 8: MMA issuer, 9: B loader
 
@@ -531,8 +539,9 @@ __global__ void __launch_bounds__(FH_THREADS, 1) forward_h_kernel(FwdHArgs a) {
       }
     }
   } else if (warp == 8) {
-    if (lane == 0) {
+    {
       // kind::f16, fp16 x fp16 -> fp32, both K-major, N = NT, M = 128
+      const bool issuer = elect_one();
       const uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(FT_TM >> 4) << 24);
       const uint64_t adesc0 = make_desc(smem_u32(a_t), 16, 1024, 2), bdesc0 = make_desc(smem_u32(bst), 16, 1024, 2);
       int it = 0;
@@ -549,14 +558,17 @@ __global__ void __launch_bounds__(FH_THREADS, 1) forward_h_kernel(FwdHArgs a) {
           const uint64_t ahi = adesc0 + (uint64_t)(q * 1024), alo = ahi + 2048;
           const uint64_t bhi = bdesc0 + (uint64_t)(s * (STAGE_BYTES >> 4)), blo = bhi + (IMG_BYTES >> 4);
           const int ksteps = min(4, (dn - q * FH_KCH + 15) / 16);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            umma_f16(d, ahi + 2 * ks, bhi + 2 * ks, idesc, (q > 0 || ks > 0) ? 1u : 0u);
-            umma_f16(d, alo + 2 * ks, bhi + 2 * ks, idesc, 1u);
-            umma_f16(d, ahi + 2 * ks, blo + 2 * ks, idesc, 1u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (ks < ksteps && issuer) {
+              umma_f16(d, ahi + 2 * ks, bhi + 2 * ks, idesc, (q > 0 || ks > 0) ? 1u : 0u);
+              umma_f16(d, alo + 2 * ks, bhi + 2 * ks, idesc, 1u);
+              umma_f16(d, ahi + 2 * ks, blo + 2 * ks, idesc, 1u);
+            }
           }
-          umma_commit(&b_empty[s]);
+          if (issuer) umma_commit(&b_empty[s]);
         }
-        umma_commit(&acc_full[b]);
+        if (issuer) umma_commit(&acc_full[b]);
       }
     }
   } else {
@@ -658,8 +670,310 @@ __global__ void __launch_bounds__(FH_THREADS, 1) forward_h_kernel(FwdHArgs a) {
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---- the same contraction by CTA PAIRS (tcgen05 cta_group::2): two CTAs of a cluster hold two image tiles (M = 256) and HALF
+// of every B image each (80 of the 160 columns of a tile, 20 KB per stage instead of 40), the leader issues one MMA for
+// both.  Per SM the shared-memory operand fetch drops from 115 to 81 B/clk and the TMA fill from 42 to 21 B/clk (the
+// single-CTA kernel is bound by their sum against 128 B/clk and by a 3-stage ring that barely covers the L2 latency: the
+// same shared memory now holds 6 stages).  Hand-shakes: each CTA's loader fills its own half and signals its own b_full;
+// the peer's idle MMA warp relays its b_full to the leader's peer_full (a bulk copy cannot signal another CTA's mbarrier);
+// tcgen05.commit multicasts b_empty / acc_full to both CTAs; the peer's epilogue warps arrive on the LEADER's acc_empty.
+// Accumulators: each CTA's TMEM holds its own 128 rows, so the epilogue is unchanged.
+constexpr int FH2_STAGES = 6;
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {       // acquire at cluster scope (remote arrivals)
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {          // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int L, int ND>
+__global__ void __launch_bounds__(FH_THREADS, 1) forward_h2_kernel(FwdHArgs a) {
+  constexpr int NT = 16 * L, KPT = 8 / ND;             // KPT: far-bond indices per tile
+  constexpr int IMG_BYTES = NT * 128;                // one (hi | lo) B image: NT rows x 64 fp16
+  constexpr int HALF_BYTES = IMG_BYTES / 2;          // this CTA's 80 rows of one (hi | lo) image
+  constexpr int STAGE_BYTES = 2 * HALF_BYTES, STAGE_BYTES_G = 2 * IMG_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * NT <= 64 ? 64 : 2 * NT <= 128 ? 128 : 2 * NT <= 256 ? 256 : 512;
+  constexpr int NSTAGE_WARPS = 9;                    // everyone but the loader stages the A tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_t = smem;
+  uint8_t* bst = smem + FH_A_BYTES;
+  constexpr int NS = FH2_STAGES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bst + NS * STAGE_BYTES);
+  uint64_t* b_full = bars, *b_empty = bars + NS, *peer_full = bars + 2 * NS, *acc_full = bars + 3 * NS, *acc_empty = bars + 3 * NS + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * NS + 6);
+  int* rexp = reinterpret_cast<int*>(bars + 3 * NS + 8);      // [128] row exponents
+  float* xch = reinterpret_cast<float*>(rexp + FT_TM);               // [128][L] partial logits of the second column half
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Ds = a.Ds;
+  int* s_last = reinterpret_cast<int*>(xch + FT_TM * L);
+  const int dn = __ldg(a.d_near), df = __ldg(a.d_far);
+  const int nchunks = (dn + FH_KCH - 1) / FH_KCH;
+  const int ntiles_all = (df + KPT - 1) / KPT;
+  // image tile and column-tile range [j0, j0 + ntiles) of this CTA
+  const int crank = (int)cluster_ctarank();
+  const bool leader = crank == 0;
+  const int pair = (int)blockIdx.x >> 1;
+  int rt = 2 * pair + crank, part = 0, j0 = 0, ntiles = ntiles_all;
+  const bool partial = 2 * pair >= a.n_full && a.parts > 1;
+  if (partial) {
+    const int u = pair - a.n_full / 2;
+    rt = a.n_full + 2 * (u / a.parts) + crank; part = u % a.parts;
+    j0 = min(part * a.tpp, ntiles_all);
+    ntiles = min(ntiles_all, j0 + a.tpp) - j0;
+  }
+  const int64_t t0 = (int64_t)rt * FT_TM;
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); mbar_init(&peer_full[s], 1); }
+    for (int b = 0; b < 3; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 16); }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc2(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();               // barriers initialised, TMEM allocated: the B loader may start right away
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- A tile (warps 0-8; warp 9 is already streaming B images): one image row per (warp, iteration), lane = 4
+  //      consecutive k; all global loads are issued before the first use, row maximum by shuffle, scaled fp16 hi/lo
+  if (warp < NSTAGE_WARPS) {
+    constexpr int ROWS_PER_WARP = (FT_TM + NSTAGE_WARPS - 1) / NSTAGE_WARPS;
+    const int k = 4 * lane;
+    float4 v[ROWS_PER_WARP];
+#pragma unroll
+    for (int u = 0; u < ROWS_PER_WARP; ++u) {
+      const int t = warp + NSTAGE_WARPS * u;
+      const int64_t tg = t0 + t;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < FT_TM && tg < a.B && k < Ds) v[u] = __ldg(reinterpret_cast<const float4*>(a.e_near + tg * Ds + k));
+    }
+#pragma unroll
+    for (int u = 0; u < ROWS_PER_WARP; ++u) {
+      const int t = warp + NSTAGE_WARPS * u;
+      if (t >= FT_TM) continue;       // warp-uniform
+      float mx = fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const int ex = (mx > 0.f && mx < 3.0e38f) ? exponent_of(mx) - FH_TROW : 0;
+      if (lane == 0) rexp[t] = ex;
+      if (k < nchunks * FH_KCH) {
+        const float x0 = scale_pow2(v[u].x, -ex), x1 = scale_pow2(v[u].y, -ex), x2 = scale_pow2(v[u].z, -ex), x3 = scale_pow2(v[u].w, -ex);
+        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+        const uint32_t off = (uint32_t)((k >> 6) * 16384) + k128_chunk_off(t, (k & 63) >> 3) + (uint32_t)((lane & 1) * 8);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(a_t + off) = hv;
+        *reinterpret_cast<uint2*>(a_t + 2 * 16384 + off) = lv;
+      }
+    }
+    fence_async_proxy();
+  }
+  // both A tiles staged, every barrier of the pair initialised: one cluster barrier (the loader has already started: its
+  // first stages only touch this CTA's own barriers)
+  if (warp == 9 && lane == 0) {
+    const int total = ntiles * nchunks;
+    for (int it = 0; it < NS && it < total; ++it) {
+      const int j = it / nchunks, q = it % nchunks;
+      mbar_expect_tx(&b_full[it], STAGE_BYTES);
+      const uint8_t* src = a.bimg + ((int64_t)(j0 + j) * a.nchunks_max + q) * STAGE_BYTES_G + (size_t)crank * HALF_BYTES;
+      bulk_g2s(bst + it * STAGE_BYTES, src, HALF_BYTES, &b_full[it]);
+      bulk_g2s(bst + it * STAGE_BYTES + HALF_BYTES, src + IMG_BYTES, HALF_BYTES, &b_full[it]);
+    }
+  }
+  __syncwarp();
+  cluster_sync_all();
+  tc_fence_after();
+
+  if (warp == 9) {
+    if (lane == 0) {
+      int it = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        for (int q = 0; q < nchunks; ++q, ++it) {
+          if (it < NS) continue;                           // issued before the cluster barrier
+          const int s = it % NS, ph = (it / NS) & 1;
+          mbar_wait(&b_empty[s], (uint32_t)(ph ^ 1));
+          mbar_expect_tx(&b_full[s], STAGE_BYTES);
+          const uint8_t* src = a.bimg + ((int64_t)(j0 + j) * a.nchunks_max + q) * STAGE_BYTES_G + (size_t)crank * HALF_BYTES;
+          bulk_g2s(bst + s * STAGE_BYTES, src, HALF_BYTES, &b_full[s]);
+          bulk_g2s(bst + s * STAGE_BYTES + HALF_BYTES, src + IMG_BYTES, HALF_BYTES, &b_full[s]);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0 && !leader) {
+      // relay: this CTA's half of a stage has landed -> the leader's peer_full
+      const int total = ntiles * nchunks;
+      for (int it = 0; it < total; ++it) {
+        const int s = it % NS, ph = (it / NS) & 1;
+        mbar_wait(&b_full[s], (uint32_t)ph);
+        mbar_arrive_remote(mapa_u32(smem_u32(&peer_full[s]), 0));
+      }
+    } else if (leader) {
+      // kind::f16, fp16 x fp16 -> fp32, both K-major, N = NT, M = 256 over the CTA pair
+      const bool issuer = elect_one();
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint64_t adesc0 = make_desc(smem_u32(a_t), 16, 1024, 2), bdesc0 = make_desc(smem_u32(bst), 16, 1024, 2);
+      int it = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        const int b = j % 3;                 // three accumulators (480 of the 512 TMEM columns): the peer's drain is a cluster hop away
+        if (j >= 3) mbar_wait_cluster(&acc_empty[b], (uint32_t)((j / 3 - 1) & 1));
+        tc_fence_after();
+        const uint32_t d = tmem_base + b * NT;
+        for (int q = 0; q < nchunks; ++q, ++it) {
+          const int s = it % NS, ph = (it / NS) & 1;
+          mbar_wait(&b_full[s], (uint32_t)ph);
+          mbar_wait_cluster(&peer_full[s], (uint32_t)ph);
+          tc_fence_after();
+          const uint64_t ahi = adesc0 + (uint64_t)(q * 1024), alo = ahi + 2048;
+          const uint64_t bhi = bdesc0 + (uint64_t)(s * (STAGE_BYTES >> 4)), blo = bhi + (HALF_BYTES >> 4);
+          const int ksteps = min(4, (dn - q * FH_KCH + 15) / 16);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (ks < ksteps && issuer) {
+              umma2_f16(d, ahi + 2 * ks, bhi + 2 * ks, idesc, (q > 0 || ks > 0) ? 1u : 0u);
+              umma2_f16(d, alo + 2 * ks, bhi + 2 * ks, idesc, 1u);
+              umma2_f16(d, ahi + 2 * ks, blo + 2 * ks, idesc, 1u);
+            }
+          }
+          if (issuer) umma2_commit(&b_empty[s]);
+        }
+        if (issuer) umma2_commit(&acc_full[b]);
+      }
+    }
+  } else {
+    // ===== epilogue: warp = (column half, TMEM lane quadrant); one image row per thread, half of the tile's columns.
+    //       One warp per scheduler was latency bound (2400 cycles per tile against 1920 of MMAs); two halve it.
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
+    const int64_t tg = t0 + row;
+    const bool live = tg < a.B;
+    float pp[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      const float2 p1 = __ldg(reinterpret_cast<const float2*>(a.phi_near) + tg);
+      if (ND == 2) {
+        const float2 p2 = __ldg(reinterpret_cast<const float2*>(a.phi_far) + tg);
+        pp[0] = p1.x * p2.x; pp[1] = p1.x * p2.y; pp[2] = p1.y * p2.x; pp[3] = p1.y * p2.y;   // index m*2+n
+      } else {
+        pp[0] = p1.x; pp[1] = p1.y;                                                             // index m
+      }
+    }
+    float facc[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) facc[l] = 0.f;
+    // far-environment entries of my row, fetched two tiles ahead: the load latency (~1 us) must not sit between the
+    // accumulator becoming ready and its drain
+    struct EK { float4 v[KPT / 4]; };
+    auto load_e = [&](int j) {
+      EK e;
+#pragma unroll
+      for (int u = 0; u < KPT / 4; ++u) {
+        e.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && j < ntiles && KPT * (j0 + j) + 4 * u < Ds) e.v[u] = __ldg(reinterpret_cast<const float4*>(a.e_far + tg * Ds + KPT * (j0 + j) + 4 * u));
+      }
+      return e;
+    };
+    EK e_cur = load_e(0), e_nxt = load_e(1);
+    for (int j = 0; j < ntiles; ++j) {
+      const int b = j % 3;
+      const EK e_nn = load_e(j + 2);
+      float ek[KPT];
+#pragma unroll
+      for (int u = 0; u < KPT / 4; ++u) { ek[4 * u] = e_cur.v[u].x; ek[4 * u + 1] = e_cur.v[u].y; ek[4 * u + 2] = e_cur.v[u].z; ek[4 * u + 3] = e_cur.v[u].w; }
+      e_cur = e_nxt; e_nxt = e_nn;
+      mbar_wait(&acc_full[b], (uint32_t)((j / 3) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * NT);
+      if (half == 0) fh_epilogue_tile<L, 0, ND>(taddr, pp, ek, facc);
+      else fh_epilogue_tile<L, 1, ND>(taddr, pp, ek, facc);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (leader) mbar_arrive(&acc_empty[b]); else mbar_arrive_remote(mapa_u32(smem_u32(&acc_empty[b]), 0)); }
+    }
+    // combine the two column halves, undo both scalings (exact powers of two)
+    if (half == 1) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) xch[row * L + l] = facc[l];
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    if (half == 0) {
+      const int ex = rexp[row] + bond_exponent(a.maxbits);
+      if (!partial) {
+        if (live) {
+#pragma unroll
+          for (int l = 0; l < L; ++l) a.f[tg * L + l] = scale_pow2(facc[l] + xch[row * L + l], ex);
+        }
+      } else {
+        const int rloc = rt - a.n_full;
+        float* mine = a.pscr + ((size_t)(rloc * a.parts + part) * FT_TM + row) * L;
+        if (live) {
+#pragma unroll
+          for (int l = 0; l < L; ++l) __stcg(&mine[l], scale_pow2(facc[l] + xch[row * L + l], ex));
+        }
+        __threadfence();
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+        if (tid == 0) {
+          const int old = atomicAdd(&a.pcnt[rloc], 1);
+          const int last = old == a.parts - 1;
+          if (last) a.pcnt[rloc] = 0;               // ready for the next launch
+          *s_last = last;
+        }
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+        if (*s_last && live) {
+          __threadfence();
+          float sum[L];
+#pragma unroll
+          for (int l = 0; l < L; ++l) sum[l] = 0.f;
+          for (int pq = 0; pq < a.parts; ++pq) {           // fixed order, whoever arrives last
+            const float* src = a.pscr + ((size_t)(rloc * a.parts + pq) * FT_TM + row) * L;
+#pragma unroll
+            for (int l = 0; l < L; ++l) sum[l] += __ldcg(&src[l]);
+          }
+#pragma unroll
+          for (int l = 0; l < L; ++l) a.f[tg * L + l] = sum[l];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2(tmem_base, TMEM_COLS);
+}
+
 template <int L>
 size_t forward_h_smem() { return (size_t)FH_A_BYTES + (size_t)FT_STAGES * 2 * 16 * L * 128 + 1024 + (size_t)FT_TM * L * 4 + 1024; }
+
+template <int L>
+size_t forward_h2_smem() { return (size_t)FH_A_BYTES + (size_t)FH2_STAGES * 16 * L * 128 + 1024 + (size_t)FT_TM * L * 4 + 1024; }
 
 template <int L>
 size_t forward_tc_smem() { return (size_t)2 * FT_A_BYTES + (size_t)FT_STAGES * 2 * 16 * 16 * L * 4 + 256 + 1024; }
@@ -678,13 +992,16 @@ int64_t forward_tc_image_floats(int Ds, int L) {
 
 // how the image tiles of a launch are spread over the SMs: full waves of whole tiles, then the remaining `rem` tiles split
 // by columns over parts = floor(sms / rem) CTAs each (at most FH_PARTS_MAX and one column tile per CTA)
-static void forward_h_tail(int64_t B, int ntiles_cols, FwdHArgs& h, unsigned& grid, uint8_t* img_end) {
+// pairs: the kernel runs as clusters of two CTAs (two image tiles per cluster): whole waves of sms / 2 pairs, the tail split per pair
+static void forward_h_tail(int64_t B, int ntiles_cols, FwdHArgs& h, unsigned& grid, uint8_t* img_end, bool pairs = false) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   if (sms > FH_TAIL_MAX) sms = FH_TAIL_MAX;
+  if (pairs) sms &= ~1;
   const int64_t rtiles = ceil_div64(B, FT_TM);
   const int rem = (int)(rtiles % sms);
-  int parts = rem > 0 ? sms / rem : 1;
+  const int rem_units = pairs ? (rem + 1) / 2 : rem, units = pairs ? sms / 2 : sms;      // CTAs or CTA pairs
+  int parts = rem_units > 0 ? units / rem_units : 1;
   if (parts > FH_PARTS_MAX) parts = FH_PARTS_MAX;
   if (parts > ntiles_cols) parts = ntiles_cols;
   if (parts < 1) parts = 1;
@@ -693,7 +1010,32 @@ static void forward_h_tail(int64_t B, int ntiles_cols, FwdHArgs& h, unsigned& gr
   h.tpp = (ntiles_cols + parts - 1) / parts;
   h.pcnt = reinterpret_cast<int32_t*>(img_end) + 16;                 // right behind the bond exponent word (cleared with it)
   h.pscr = reinterpret_cast<float*>(img_end) + 16 + FH_PCNT;
-  grid = (unsigned)(h.n_full + (int64_t)rem * parts);
+  grid = pairs ? (unsigned)(h.n_full + 2 * (int64_t)rem_units * parts) : (unsigned)(h.n_full + (int64_t)rem * parts);
+}
+
+// launch of the CTA-pair kernel (clusters of 2); false if this device cannot schedule it (the caller then takes the single-CTA kernel)
+template <int ND>
+static int launch_forward_h2(FwdHArgs& h, int64_t B, int ntiles_cols, uint8_t* tail_base, cudaStream_t st, bool& done) {
+  done = false;
+  static int ok = -1;
+  const size_t smem = forward_h2_smem<10>();
+  if (ok < 0) {
+    ok = cudaFuncSetAttribute(forward_h2_kernel<10, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess ? 1 : 0;
+    (void)cudaGetLastError();
+  }
+  if (!ok) return TRMPS_OK;
+  unsigned grid = 0;
+  forward_h_tail(B, ntiles_cols, h, grid, tail_base, true);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  TRMPS_CUDA_OK(cudaLaunchKernelEx(&cfg, forward_h2_kernel<10, ND>, h));
+  count_launch();
+  done = true;
+  return TRMPS_OK;
 }
 
 // where the fp16 forward keeps the bits of the largest |bond entry| (two-site form): a kernel that produces the bond may fill
@@ -732,6 +1074,11 @@ int launch_forward_tc(const float* e_near, const float* e_far, const float* phi_
     if (!attr_h) {
       TRMPS_CUDA_OK(cudaFuncSetAttribute(forward_h_kernel<10, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
       attr_h = true;
+    }
+    if (option_value(6) != 0) {
+      bool done = false;
+      int rc = launch_forward_h2<2>(h, B, ntiles, reinterpret_cast<uint8_t*>(maxbits), st, done);
+      if (rc || done) return rc;
     }
     unsigned grid = 0;
     forward_h_tail(B, ntiles, h, grid, reinterpret_cast<uint8_t*>(maxbits));
@@ -784,9 +1131,15 @@ int launch_forward_site_tc(const float* e_near, const float* e_far, const float*
     TRMPS_CUDA_OK(cudaFuncSetAttribute(forward_h_kernel<10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
     attr_h = true;
   }
-  unsigned grid = 0;
   // (the arrival counters and the partial logits of the tail tiles sit behind the TWO-site image, whichever form runs)
-  forward_h_tail(B, ntiles, h, grid, img + (size_t)((Ds + 3) / 4) * nchunks * 2 * 16 * L * 128);
+  uint8_t* tail_base = img + (size_t)((Ds + 3) / 4) * nchunks * 2 * 16 * L * 128;
+  if (option_value(6) != 0) {
+    bool done = false;
+    int rc = launch_forward_h2<1>(h, B, ntiles, tail_base, st, done);
+    if (rc || done) return rc;
+  }
+  unsigned grid = 0;
+  forward_h_tail(B, ntiles, h, grid, tail_base);
   forward_h_kernel<10, 1><<<grid, FH_THREADS, smem_h, st>>>(h);
   TRMPS_LAUNCH_OK("forward_h_kernel");
   return TRMPS_OK;

@@ -225,8 +225,11 @@ __global__ void __launch_bounds__(GH_THREADS, 1) grad_h_kernel(GradHArgs g) {
       fence_async_proxy();          // make the generic-proxy stores visible to the tensor core (async proxy)
       mbar_arrive(&full[s]);
     }
-  } else if (tid == GH_FORMERS) {
-    // ===== MMA issuer =====
+  } else if (tid >= GH_FORMERS) {
+    // ===== MMA issuer: the whole warp runs the loop (uniform descriptor arithmetic), one elected lane issues =====
+    uint32_t el_;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(el_));
+    const bool issuer = el_ != 0;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(GH_TN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f16 x f16 -> f32, K-major
     for (int ch = 0; ch < nch; ++ch) {
       const int s = ch % GH_STAGES, it = ch / GH_STAGES;
@@ -241,13 +244,13 @@ __global__ void __launch_bounds__(GH_THREADS, 1) grad_h_kernel(GradHArgs g) {
         for (int mt = 0; mt < 2; ++mt) {
           const uint64_t ro = (uint64_t)(mt * (128 * 64 >> 4) + 2 * ks);       // rows 128.. of the A tile; +2 units per K=16
           const uint32_t d = tmem_base + mt * GH_TN;
-          umma_f16(d, a_hi + ro, b_hi + 2 * ks, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
-          umma_f16(d, a_lo + ro, b_hi + 2 * ks, idesc, 1u);
-          umma_f16(d, a_hi + ro, b_lo + 2 * ks, idesc, 1u);
+          if (issuer) umma_f16(d, a_hi + ro, b_hi + 2 * ks, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
+          if (issuer) umma_f16(d, a_lo + ro, b_hi + 2 * ks, idesc, 1u);
+          if (issuer) umma_f16(d, a_hi + ro, b_lo + 2 * ks, idesc, 1u);
         }
       }
-      umma_commit(&bars[s]);                          // stage s may be overwritten once these MMAs have read it
-      if (ch == nch - 1) umma_commit(&bars[GH_STAGES]);
+      if (issuer) umma_commit(&bars[s]);                          // stage s may be overwritten once these MMAs have read it
+      if (ch == nch - 1 && issuer) umma_commit(&bars[GH_STAGES]);
     }
   }
 

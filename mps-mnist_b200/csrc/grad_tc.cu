@@ -235,8 +235,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
     mbar_arrive(&full[s]);        // no block barrier: the issuer warp waits for all producers on the stage's mbarrier
     tick(4);
   };
-  // MMAs of one chunk (issuer thread)
-  auto issue_chunk = [&](int ch) {
+  // MMAs of one chunk: the whole issuer warp runs this (uniform control flow and descriptor arithmetic, which the compiler
+  // keeps in the uniform datapath), one elected lane issues -- under `if (tid == TC_FORMERS)` every descriptor was a
+  // per-thread value moved to the uniform registers MMA by MMA (ELECT + R2UR.BROADCAST), ~150 cycles between MMAs
+  auto issue_chunk = [&](int ch, bool issuer) {
     const int s = ch % TC_STAGES, it = ch / TC_STAGES;
     uint8_t* st = smem + s * TC_STAGE_BYTES;
     uint8_t* a_hi = st, *a_lo = st + TC_A_BYTES, *b_hi = st + 2 * TC_A_BYTES, *b_lo = st + 2 * TC_A_BYTES + TC_B_BYTES;
@@ -255,13 +257,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
         const uint64_t dal = make_desc_mn_sw128(smem_u32(a_lo) + koffA + moff, TC_ATOM, (TC_TM / 32) * TC_ATOM);
         const uint32_t d = tmem_base + mt * TC_TN;
         const uint32_t acc = (kb > 0) ? 1u : acc0;
-        umma_tf32(d, dah, dbh, idesc, acc);
-        umma_tf32(d, dal, dbh, idesc, 1u);
-        umma_tf32(d, dah, dbl, idesc, 1u);
+        if (issuer) {
+          umma_tf32(d, dah, dbh, idesc, acc);
+          umma_tf32(d, dal, dbh, idesc, 1u);
+          umma_tf32(d, dah, dbl, idesc, 1u);
+        }
       }
     }
-    umma_commit(&bars[s]);                          // stage s may be overwritten once these MMAs have read it
-    if (ch == nch - 1) umma_commit(&bars[TC_STAGES]);
+    if (issuer) {
+      umma_commit(&bars[s]);                          // stage s may be overwritten once these MMAs have read it
+      if (ch == nch - 1) umma_commit(&bars[TC_STAGES]);
+    }
   };
 
   // software pipeline: the global loads of chunks ch+1 and ch+2 are in flight while chunk ch is converted and stored
@@ -278,8 +284,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) grad_tc_kernel(GradTcArgs g) {
         if (ch + 3 < nch) load_chunk(ch + 3, ra1, rb1, pa1, pb1);
       }
     }
-  } else if (tid == TC_FORMERS) {
-    for (int ch = 0; ch < nch; ++ch) issue_chunk(ch);
+  } else {
+    uint32_t el;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(el));
+    const bool issuer = el != 0;
+    for (int ch = 0; ch < nch; ++ch) issue_chunk(ch, issuer);
   }
 
   if (timer) for (int k = 0; k < 6; ++k) g.dbg[k] = (float)tacc[k];

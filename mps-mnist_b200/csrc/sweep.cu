@@ -55,7 +55,8 @@ static int g_fwd_impl = 0;    // same for the forward contraction
 static int g_chain_impl = 0;  // 0 = fused tcgen05 chain for inference when Ds <= 32, 1 = per-site FP32 SIMT steps
 static int g_fwd_site = 1;    // first forward of a two-site update in its single-site form (needs the cached environment of the same site: trmps_sweep_init_env / sweeps provide it)
 static int g_env_impl = 0;    // environments of the sweep: 0 = tcgen05 chain from / to HBM, 1 = per-site FP32 SIMT steps
-int option_value(int option) { return option == 0 ? g_grad_impl : option == 1 ? g_fwd_impl : g_chain_impl; }
+static int g_fwd_pair = 0;    // fp16 forward by CTA pairs (tcgen05 cta_group::2): parity-tested, measured slower than one CTA per tile
+int option_value(int option) { return option == 0 ? g_grad_impl : option == 1 ? g_fwd_impl : option == 6 ? g_fwd_pair : g_chain_impl; }
 
 // SM count of the CURRENT device (ranks above 0 of a multi-GPU process group run on other devices; the attribute query
 // is a host-side table lookup)
@@ -514,6 +515,7 @@ extern "C" int trmps_set_option(int32_t option, int32_t value) {
   if (option == 3 && value >= 0 && value <= 3) { set_flat_variant(value); return TRMPS_OK; }
   if (option == 4 && (value == 0 || value == 1)) { g_env_impl = value; return TRMPS_OK; }
   if (option == 5 && (value == 0 || value == 1)) { g_fwd_site = value; return TRMPS_OK; }
+  if (option == 6 && (value == 0 || value == 1)) { g_fwd_pair = value; return TRMPS_OK; }
   set_error("trmps_set_option: unknown option %d / value %d", option, value);
   return TRMPS_E_ARG;
 }

@@ -225,6 +225,31 @@ def site_form(request):
     nat.set_option(5, 1)
 
 
+@pytest.mark.parametrize("B", [400, 1000, 300 * 128 + 77])
+def test_forward_by_cta_pairs_equals_one_cta_per_tile(B):
+    """trmps_set_option(6, 1): the fp16 forward as clusters of two CTAs (tcgen05 cta_group::2, half of every bond image per CTA,
+    relayed mbarrier hand-shake) issues the same MMAs in the same order: bit-identical logits, for batches with an odd number
+    of image tiles, a column-split tail and more than one wave, in both forms of the forward (a whole bond update)."""
+    N, L, loc = 8, 10, 3
+    pix, phi, lab, nodes, loc = make_case(N, B, L, 0, seed=43, loc=loc)
+    outs = []
+    for pair in (0, 1):
+        nat.set_option(6, pair)
+        try:
+            st = make_state(N, B, L, 24, nodes, loc, phi, lab)
+            st.init_env(loc)
+            st.bond_merge(loc, +1)
+            st.bond_forward(loc, +1, 0)
+            f_bond = st.work[st.layout.f0: st.layout.f0 + B * L].clone()
+            st.bond_step(loc, +1, dev.make_opt(lr=0.05, max_size=24))
+            torch.cuda.synchronize()
+            outs.append((f_bond, st.scalars().clone(), st.special.clone()))
+        finally:
+            nat.set_option(6, 0)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
 @pytest.mark.parametrize("site_form", [1, 0], indirect=True)
 @pytest.mark.parametrize("loss", [o.SOFTMAX_XENT, o.SQUARED])
 @pytest.mark.parametrize("updates", [1, 3])
