@@ -758,6 +758,8 @@ __global__ void __launch_bounds__(CC_T) split_chol_cluster_kernel(CholCArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) double ccs[];
   __shared__ __align__(8) uint64_t pbar[16];
+  __shared__ __align__(8) uint64_t hbar;                   // the HEAD of the last block to the left (this CTA's diagonal rows) has arrived
+  __shared__ __align__(16) double Hd[CW * CC_LD];           // ... and the head itself
   __shared__ double rinv_s[CW];
   __shared__ double red[CC_T / 32];
   __shared__ float nrm_part[CW][SP_NMAX / 32];
@@ -779,6 +781,7 @@ __global__ void __launch_bounds__(CC_T) split_chol_cluster_kernel(CholCArgs a) {
   if (tid < CW && tid < J) {
     mbar_init_cta(&pbar[tid], 1);
   }
+  if (tid == 0) mbar_init_cta(&hbar, 1);
   __syncthreads();
   dmax = 0.0;
   for (int q = 0; q < CC_T / 32; ++q) dmax = fmax(dmax, red[q]);
@@ -788,6 +791,8 @@ __global__ void __launch_bounds__(CC_T) split_chol_cluster_kernel(CholCArgs a) {
   if (dmax > 0.0) frexp(sqrt(dmax), &ex);
   const double inv_scale = ldexp(1.0, -ex);
   if (active && tid < J) mbar_expect_tx_cta(&pbar[tid], (uint32_t)nrows * CC_LD * 8u);
+  const int hrows = min(CW, nrows);                        // rows of the head piece (this CTA's diagonal rows)
+  if (active && J > 0 && tid == 0) mbar_expect_tx_cta(&hbar, (uint32_t)hrows * CC_LD * 8u);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   // own block of G (stored in full and symmetric: column r0 + c read as row r0 + c, unit stride in li)
   for (int e = tid; e < CW * SP_NMAX; e += CC_T) {
@@ -798,29 +803,49 @@ __global__ void __launch_bounds__(CC_T) split_chol_cluster_kernel(CholCArgs a) {
   cluster_arrive_release();
   cluster_wait_acquire();
   if (active) {
-    // ---- contributions of the column blocks to the left
-    for (int K = 0; K < J; ++K) {
-      mbar_wait_cta(&pbar[K], 0);
-      const double* Pk = P + (size_t)K * nrows * CC_LD;
-      if (tid < nrows) {
-        double pr[CW], acc[CW];
+    // ---- contributions of the column blocks to the left.  The last one (K = J - 1) is on the critical path of the whole
+    //      factorisation -- CTA J - 1 has only just finished it -- so it comes in two parts: a HEAD (its rows of this CTA's
+    //      diagonal block, 2 KB, sent first) that all 256 threads apply to the diagonal block at once, after which warp 0
+    //      factorises the diagonal block while warps 1-7 apply the full piece to the rows below
+    auto update_row = [&](const double* Pk, int li) {
+      double pr[CW], acc[CW];
+#pragma unroll
+      for (int t = 0; t < CW; t += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(&Pk[li * CC_LD + t]);
+        pr[t] = v.x; pr[t + 1] = v.y;
+      }
+#pragma unroll
+      for (int c = 0; c < CW; ++c) {
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int t = 0; t < CW; t += 2) {
-          const double2 v = *reinterpret_cast<const double2*>(&Pk[tid * CC_LD + t]);
-          pr[t] = v.x; pr[t + 1] = v.y;
+          const double2 v = *reinterpret_cast<const double2*>(&Pk[c * CC_LD + t]);      // L[r0 + c][16 K + t], broadcast
+          s0 = fma(pr[t], v.x, s0); s1 = fma(pr[t + 1], v.y, s1);
         }
+        acc[c] = s0 + s1;
+      }
 #pragma unroll
-        for (int c = 0; c < CW; ++c) {
+      for (int c = 0; c < CW; ++c) A[li * CC_LD + c] -= acc[c];
+    };
+    for (int K = 0; K + 1 < J; ++K) {
+      mbar_wait_cta(&pbar[K], 0);
+      if (tid < nrows) update_row(P + (size_t)K * nrows * CC_LD, tid);
+    }
+    if (J > 0) {
+      mbar_wait_cta(&hbar, 0);
+      __syncthreads();                                     // the earlier updates of the diagonal rows are in shared memory
+      {
+        const int r = tid >> 4, c = tid & 15;              // one entry of the diagonal block per thread
+        if (r < hrows && c < hrows) {
           double s0 = 0.0, s1 = 0.0;
 #pragma unroll
           for (int t = 0; t < CW; t += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(&Pk[c * CC_LD + t]);      // L[r0 + c][16 K + t], broadcast
-            s0 = fma(pr[t], v.x, s0); s1 = fma(pr[t + 1], v.y, s1);
+            const double2 x = *reinterpret_cast<const double2*>(&Hd[r * CC_LD + t]);
+            const double2 y = *reinterpret_cast<const double2*>(&Hd[c * CC_LD + t]);
+            s0 = fma(x.x, y.x, s0); s1 = fma(x.y, y.y, s1);
           }
-          acc[c] = s0 + s1;
+          A[r * CC_LD + c] -= s0 + s1;
         }
-#pragma unroll
-        for (int c = 0; c < CW; ++c) A[tid * CC_LD + c] -= acc[c];
       }
     }
     __syncthreads();
@@ -849,6 +874,12 @@ __global__ void __launch_bounds__(CC_T) split_chol_cluster_kernel(CholCArgs a) {
 #pragma unroll
         for (int c = 0; c < CW; ++c) A[r * CC_LD + c] = c <= r ? d[c] : 0.0;
       }
+    } else if (J > 0) {
+      // warps 1-7 meanwhile: the full last piece applied to the rows below the diagonal block (at most 224 of them);
+      // its first 16 rows are the head again (already applied to the diagonal block)
+      mbar_wait_cta(&pbar[J - 1], 0);
+      const int li = tid - 32 + CW;
+      if (li < nrows) update_row(P + (size_t)(J - 1) * nrows * CC_LD, li);
     }
     __syncthreads();
     // ---- rows below: forward substitution with the factor of the diagonal block
@@ -873,6 +904,13 @@ __global__ void __launch_bounds__(CC_T) split_chol_cluster_kernel(CholCArgs a) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
+      if (lane == 0 && J + 1 < NB) {
+        // head: the next CTA's diagonal rows (rows 16 .. of this block), first in the queue
+        const int hr = min(CW, n - CW * (J + 1));
+        bulk_row_to_cta(map_to_cta(smem_addr(Hd), J + 1), smem_addr(A + (size_t)CW * CC_LD), (uint32_t)hr * CC_LD * 8u,
+                        map_to_cta(smem_addr(&hbar), J + 1));
+      }
+      __syncwarp();
       const int Jd = J + 1 + lane;
       if (Jd < NB) {
         const int nr_d = n - CW * Jd;
