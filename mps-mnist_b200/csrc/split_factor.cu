@@ -73,6 +73,7 @@ constexpr int GT = 64, GK = 32, GLD = GT + 2;
 
 struct GramArgs {
   const float* M; int R, Cc, Ds; const int32_t* d_near; int ks_cols, KS; double* gp; double* G; int32_t* cnt;
+  int finalize;      // 0: leave the column-slice partials in gp (the cluster Cholesky adds them while it loads its blocks)
 };
 
 __global__ void __launch_bounds__(256) split_gram_kernel(GramArgs a) {
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(256) split_gram_kernel(GramArgs a) {
       }
     }
   }
+  if (!a.finalize) return;
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -746,6 +748,7 @@ constexpr int CC_T = 256, CC_LD = 18;          // row stride of a block in share
 
 struct CholCArgs {
   const double* G; float* Rf; int R; const int32_t* d_near; float* scale; int32_t* rowmap; int csize;
+  const double* gp; int KS;      // KS > 0: G = sum of the KS column-slice partials gp[ks][R][R] of split_gram_kernel (lower tiles), added here in order
 };
 
 size_t chol_cluster_smem(int R) {
@@ -773,8 +776,19 @@ __global__ void __launch_bounds__(CC_T) split_chol_cluster_kernel(CholCArgs a) {
   double* A = ccs;                                         // A[li * CC_LD + c] = (trailing matrix / L)[r0 + li][r0 + c]
   double* P = ccs + (size_t)SP_NMAX * CC_LD;               // piece K: rows r0 .. n-1 of column block K, nrows x CC_LD
   // largest diagonal entry -> pivot threshold and the power-of-two scale of the FP32 copy (every CTA, same bits)
+  // entry (i, j), i >= j or both inside one diagonal block, of the Gram matrix: the slices in a fixed order (all loads in flight)
+  auto gram_at = [&](int i, int j) -> double {
+    if (a.KS <= 0) return __ldcg(&a.G[(size_t)i * R + j]);
+    double v[SP_KS_MAX];
+#pragma unroll
+    for (int ks = 0; ks < SP_KS_MAX; ++ks) v[ks] = ks < a.KS ? __ldcg(&a.gp[((size_t)ks * R + i) * R + j]) : 0.0;
+    double sum = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < SP_KS_MAX; ++ks) sum += v[ks];
+    return sum;
+  };
   double dmax = 0.0;
-  for (int i = tid; i < n; i += CC_T) dmax = fmax(dmax, __ldcg(&a.G[(size_t)i * R + i]));
+  for (int i = tid; i < n; i += CC_T) dmax = fmax(dmax, gram_at(i, i));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
   if (lane == 0) red[warp] = dmax;
@@ -794,10 +808,18 @@ __global__ void __launch_bounds__(CC_T) split_chol_cluster_kernel(CholCArgs a) {
   const int hrows = min(CW, nrows);                        // rows of the head piece (this CTA's diagonal rows)
   if (active && J > 0 && tid == 0) mbar_expect_tx_cta(&hbar, (uint32_t)hrows * CC_LD * 8u);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  // own block of G (stored in full and symmetric: column r0 + c read as row r0 + c, unit stride in li)
-  for (int e = tid; e < CW * SP_NMAX; e += CC_T) {
-    const int c = e / SP_NMAX, li = e % SP_NMAX;
-    if (li < nrows) A[li * CC_LD + c] = c < w ? __ldcg(&a.G[(size_t)(r0 + c) * R + r0 + li]) : 0.0;
+  // own block of G: rows r0 + li, columns r0 .. r0 + 15 (16 threads read one row's 128 bytes of every slice)
+  if (a.KS > 0) {
+    for (int e = tid; e < CW * SP_NMAX; e += CC_T) {
+      const int c = e % CW, li = e / CW;
+      if (li < nrows) A[li * CC_LD + c] = c < w ? gram_at(r0 + li, r0 + c) : 0.0;
+    }
+  } else {
+    // (G stored in full and symmetric: column r0 + c read as row r0 + c, unit stride in li)
+    for (int e = tid; e < CW * SP_NMAX; e += CC_T) {
+      const int c = e / SP_NMAX, li = e % SP_NMAX;
+      if (li < nrows) A[li * CC_LD + c] = c < w ? __ldcg(&a.G[(size_t)(r0 + c) * R + r0 + li]) : 0.0;
+    }
   }
   __syncthreads();
   cluster_arrive_release();
@@ -1638,8 +1660,6 @@ int split_factor(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& 
   const int per = (chunks + ks - 1) / ks;
   ga.ks_cols = per * GK;
   ga.KS = (chunks + per - 1) / per;
-  split_gram_kernel<<<dim3(ntiles, ga.KS), 256, 0, st>>>(ga);
-  TRMPS_LAUNCH_OK("split_gram_kernel");
   // 2. Cholesky: spread over a cluster (split_impl 0, when the device can schedule the cluster), else on one SM
   const int chol_csize = R <= 16 ? 1 : R <= 32 ? 2 : R <= 64 ? 4 : R <= 128 ? 8 : 16;
   static int chol_cluster_ok[17] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
@@ -1659,9 +1679,15 @@ int split_factor(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& 
     }
     (void)cudaGetLastError();
   }
-  if (opt->split_impl == 0 && chol_cluster_ok[chol_csize] == 1) {
+  const bool chol_cluster = opt->split_impl == 0 && chol_cluster_ok[chol_csize] == 1;
+  // (the cluster Cholesky adds the column slices of the Gram product itself: no last-CTA reduction pass, no G)
+  ga.finalize = chol_cluster ? 0 : 1;
+  split_gram_kernel<<<dim3(ntiles, ga.KS), 256, 0, st>>>(ga);
+  TRMPS_LAUNCH_OK("split_gram_kernel");
+  if (chol_cluster) {
     CholCArgs cc;
     cc.G = w.G; cc.Rf = w.Rf; cc.R = R; cc.d_near = g.d_near; cc.scale = w.scale; cc.rowmap = w.rowmap; cc.csize = chol_csize;
+    cc.gp = w.gp; cc.KS = ga.KS;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(chol_csize); cfg.blockDim = dim3(CC_T); cfg.dynamicSmemBytes = chol_smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
