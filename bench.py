@@ -663,12 +663,12 @@ def run_ours(args, rank, local_rank, world):
                       avg_launch_ms=grad_ms / max(grad_n, 1), launches=grad_n,
                       achieved=flops_launch * grad_n / max(grad_ms * 1e-3, 1e-12) / 1e12, peak=tf32_peak, unit="TFLOP/s",
                       traffic=62.9e6 if (B == 60000 and D == 120) else None, share_of_step=grad_ms / ms_total),
-        env=dict(kernel="env_step_kernel: one environment step with the row written back to HBM (initial build + one advance per bond)",
+        env=dict(kernel="chain_tc_kernel from / to HBM (tcgen05; env_step_kernel when the chain is not supported): one environment step with the row written back (initial build + one advance per bond)",
                  bound="hbm", avg_launch_ms=env_ms / max(env_launches, 1), launches=env_launches,
                  achieved=4.0 * (2 * D + 1) * B * env_launches / max(env_ms * 1e-3, 1e-12) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
                  traffic=None, share_of_step=env_ms / ms_total),
-        split=dict(kernel="split_gram_kernel + split_chol_kernel + split_jacobi_kernel + split_rank_kernel + split_project_kernel "
-                          "(Gram -> Cholesky -> one-sided Jacobi on the factor in one 8-CTA cluster -> U^T M)",
+        split=dict(kernel="split_gram_kernel + split_chol_cluster_kernel + split_jacobi_kernel + split_rank_kernel + split_project_kernel "
+                          "(FP64 Gram -> Cholesky spread over a thread-block cluster -> one-sided Jacobi on the factor in one cluster of up to 16 CTAs -> U^T M)",
                    bound="latency", avg_split_ms=svd_ms / max(svd_n, 1), splits=svd_n,
                    jacobi_sweeps_per_split=jacobi_sweeps / max(1.0, float(svd_n)), share_of_step=svd_ms / ms_total,
                    note="replicated on every rank and strictly sequential (bond i+1 needs its result): no bandwidth or flop roofline "
