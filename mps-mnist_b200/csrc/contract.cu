@@ -440,13 +440,47 @@ __global__ void __launch_bounds__(1024) sum_red_kernel(const float* __restrict__
 // =================================================================================================
 // per-image loss / residual                                           optimizer.py:222-227, baseoptimizer.py:347-352
 
+// one image's residual row (L floats, L even: float2 stores) and residual x feature row (2L floats: float4 stores)
+__device__ __forceinline__ void store_resid_rows(float* __restrict__ resid, float* __restrict__ sres, const float (&r)[TRMPS_LMAX], float2 pf, int L) {
+#pragma unroll
+  for (int l = 0; l < TRMPS_LMAX; l += 2) {
+    if (l < L) {
+      *reinterpret_cast<float2*>(resid + l) = make_float2(r[l], r[l + 1]);
+      *reinterpret_cast<float4*>(sres + 2 * l) = make_float4(r[l] * pf.x, r[l] * pf.y, r[l + 1] * pf.x, r[l + 1] * pf.y);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
   __shared__ float sred[32];
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int L = a.L;
   float cost_t = 0.f;
+  const bool even = (L & 1) == 0;          // rows of L floats are then 8-byte aligned: float2 / float4 accesses (L = 10: 5 instead of 10 per row)
   if (t < a.B) {
     float f[TRMPS_LMAX], y[TRMPS_LMAX];
+    if (even) {
+#pragma unroll
+      for (int l = 0; l < TRMPS_LMAX; l += 2) {
+        f[l] = f[l + 1] = 0.f; y[l] = y[l + 1] = 0.f;
+        if (l < L) {
+          float2 s;
+          if (a.from_parts) {
+            s = make_float2(0.f, 0.f);
+            for (int p = 0; p < a.nsplit; ++p) {
+              const float2 v = *reinterpret_cast<const float2*>(a.fpart + ((int64_t)p * a.B + t) * L + l);
+              s.x += v.x; s.y += v.y;
+            }
+            *reinterpret_cast<float2*>(a.f0 + t * L + l) = s;
+          } else {
+            s = *reinterpret_cast<const float2*>(a.f0 + t * L + l);
+          }
+          f[l] = s.x; f[l + 1] = s.y;
+          const float2 yy = __ldg(reinterpret_cast<const float2*>(a.labels + t * L + l));
+          y[l] = yy.x; y[l + 1] = yy.y;
+        }
+      }
+    } else {
 #pragma unroll
     for (int l = 0; l < TRMPS_LMAX; ++l) {
       f[l] = 0.f; y[l] = 0.f;
@@ -462,6 +496,7 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
         y[l] = __ldg(a.labels + t * L + l);
       }
     }
+    }
     float2 pf = __ldg(reinterpret_cast<const float2*>(a.phi_far) + t);
     if (a.loss_kind == TRMPS_LOSS_SOFTMAX_XENT) {
       float mx = -INFINITY;
@@ -471,15 +506,20 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
 #pragma unroll
       for (int l = 0; l < TRMPS_LMAX; ++l) { e[l] = l < L ? expf(f[l] - mx) : 0.f; se += e[l]; }
       const float lse = logf(se), inv = 1.f / se;
+      float rr[TRMPS_LMAX];
 #pragma unroll
       for (int l = 0; l < TRMPS_LMAX; ++l) {
+        rr[l] = 0.f;
         if (l < L) {
           float h = e[l] * inv;
           float r = y[l] - h;
+          rr[l] = r;
           cost_t += y[l] * (lse - (f[l] - mx));
-          a.resid[t * L + l] = r;
-          a.sres[t * 2 * L + 2 * l] = r * pf.x;
-          a.sres[t * 2 * L + 2 * l + 1] = r * pf.y;
+          if (!even) {
+            a.resid[t * L + l] = r;
+            a.sres[t * 2 * L + 2 * l] = r * pf.x;
+            a.sres[t * 2 * L + 2 * l + 1] = r * pf.y;
+          }
           if (a.hres) {
             float hh = h * (1.f - h);
             a.hres[t * 2 * L + 2 * l] = hh * pf.x * pf.x;
@@ -487,17 +527,24 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
           }
         }
       }
+      if (even) store_resid_rows(a.resid + t * L, a.sres + t * 2 * L, rr, pf, L);
     } else {
+      float rr[TRMPS_LMAX];
 #pragma unroll
       for (int l = 0; l < TRMPS_LMAX; ++l) {
+        rr[l] = 0.f;
         if (l < L) {
           float r = y[l] - f[l];
+          rr[l] = r;
           cost_t += r * r;
-          a.resid[t * L + l] = r;
-          a.sres[t * 2 * L + 2 * l] = r * pf.x;
-          a.sres[t * 2 * L + 2 * l + 1] = r * pf.y;
+          if (!even) {
+            a.resid[t * L + l] = r;
+            a.sres[t * 2 * L + 2 * l] = r * pf.x;
+            a.sres[t * 2 * L + 2 * l + 1] = r * pf.y;
+          }
         }
       }
+      if (even) store_resid_rows(a.resid + t * L, a.sres + t * 2 * L, rr, pf, L);
     }
   }
   float s = block_sum(cost_t, sred);
@@ -546,6 +593,25 @@ __global__ void __launch_bounds__(256) armijo_kernel(ArmijoArgs a) {
   const int L = a.L;
   float f[TRMPS_LMAX], d[TRMPS_LMAX], y[TRMPS_LMAX];
   float ysum = 0.f;
+  if ((L & 1) == 0) {
+    // rows of L floats are 8-byte aligned: float2 accesses
+#pragma unroll
+    for (int l = 0; l < TRMPS_LMAX; l += 2) {
+      f[l] = f[l + 1] = 0.f; d[l] = d[l + 1] = 0.f; y[l] = y[l + 1] = 0.f;
+      if (t < a.B && l < L) {
+        const float2 ff = *reinterpret_cast<const float2*>(a.f0 + t * L + l);
+        float2 s = make_float2(0.f, 0.f);
+        for (int p = 0; p < a.nsplit; ++p) {
+          const float2 v = *reinterpret_cast<const float2*>(a.fdpart + ((int64_t)p * a.B + t) * L + l);
+          s.x += v.x; s.y += v.y;
+        }
+        *reinterpret_cast<float2*>(a.fd + t * L + l) = s;
+        const float2 yy = __ldg(reinterpret_cast<const float2*>(a.labels + t * L + l));
+        f[l] = ff.x; f[l + 1] = ff.y; d[l] = s.x; d[l + 1] = s.y; y[l] = yy.x; y[l + 1] = yy.y;
+        ysum += yy.x; ysum += yy.y;
+      }
+    }
+  } else {
 #pragma unroll
   for (int l = 0; l < TRMPS_LMAX; ++l) {
     f[l] = 0.f; d[l] = 0.f; y[l] = 0.f;
@@ -558,6 +624,7 @@ __global__ void __launch_bounds__(256) armijo_kernel(ArmijoArgs a) {
       y[l] = __ldg(a.labels + t * L + l);
       ysum += y[l];
     }
+  }
   }
   float lr = a.lr;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -635,28 +702,41 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ sp
   const int R = 2 * Ds;
   const int64_t Cc = (int64_t)2 * L * Ds;
   float acc[4][4] = {};
+  // this thread's four elements of each tile (fixed row / column, four k-indices): addresses computed once, the loads of the
+  // NEXT k-chunk are in flight while the current one is multiplied (the kernel was a chain of exposed L2 round trips)
+  int a_row[4], a_jj[4], b_col[4], b_jj[4];
+  const float* a_ptr[4];
+  const float* b_ptr[4];
+  int64_t a_step, b_step;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int e = tid + u * 256;
+    if (dir > 0) { a_row[u] = e / KC; a_jj[u] = e % KC; b_col[u] = e % T; b_jj[u] = e / T; }
+    else { a_row[u] = e % T; a_jj[u] = e / T; b_col[u] = e / KC; b_jj[u] = e % KC; }
+    const int rg = r0 + a_row[u], kg = k0 + b_col[u];
+    a_ptr[u] = nullptr; b_ptr[u] = nullptr;
+    if (rg < R) {
+      const int m = rg / Ds, i = rg - m * Ds;
+      a_ptr[u] = dir > 0 ? sp + ((size_t)(l * 2 + m) * Ds + i) * Ds + a_jj[u] : sp + ((size_t)(l * 2 + m) * Ds + a_jj[u]) * Ds + i;
+    }
+    if (kg < Ds) b_ptr[u] = dir > 0 ? far + ((size_t)n * Ds + b_jj[u]) * Ds + kg : far + ((size_t)n * Ds + kg) * Ds + b_jj[u];
+  }
+  a_step = dir > 0 ? KC : (int64_t)KC * Ds;          // advance of the k-index by one chunk
+  b_step = dir > 0 ? (int64_t)KC * Ds : KC;
+  float ra[4], rb[4];
+  auto fetch = [&](int j0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ra[u] = (a_ptr[u] && j0 + a_jj[u] < Ds) ? __ldg(a_ptr[u] + (int64_t)(j0 / KC) * a_step) : 0.f;
+      rb[u] = (b_ptr[u] && j0 + b_jj[u] < Ds) ? __ldg(b_ptr[u] + (int64_t)(j0 / KC) * b_step) : 0.f;
+    }
+  };
+  if (mid8 > 0) fetch(0);
   for (int j0 = 0; j0 < mid8; j0 += KC) {
-    // A tile: rows r0..r0+63 (row = m*Ds+i), k-index j0..j0+15
-    for (int e = tid; e < T * KC; e += 256) {
-      int row, jj;
-      if (dir > 0) { row = e / KC; jj = e % KC; } else { row = e % T; jj = e / T; }
-      int rg = r0 + row, j = j0 + jj;
-      float v = 0.f;
-      if (rg < R && j < Ds) {
-        int m = rg / Ds, i = rg - m * Ds;
-        v = dir > 0 ? sp[((size_t)(l * 2 + m) * Ds + i) * Ds + j] : sp[((size_t)(l * 2 + m) * Ds + j) * Ds + i];
-      }
-      As[jj][row] = v;
-    }
-    for (int e = tid; e < T * KC; e += 256) {
-      int col, jj;
-      if (dir > 0) { col = e % T; jj = e / T; } else { col = e / KC; jj = e % KC; }
-      int kg = k0 + col, j = j0 + jj;
-      float v = 0.f;
-      if (kg < Ds && j < Ds) v = dir > 0 ? far[((size_t)n * Ds + j) * Ds + kg] : far[((size_t)n * Ds + kg) * Ds + j];
-      Bs[jj][col] = v;
-    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { As[a_jj[u]][a_row[u]] = ra[u]; Bs[b_jj[u]][b_col[u]] = rb[u]; }
     __syncthreads();
+    if (j0 + KC < mid8) fetch(j0 + KC);
 #pragma unroll
     for (int kk = 0; kk < KC; ++kk) {
       float av[4], bv[4];

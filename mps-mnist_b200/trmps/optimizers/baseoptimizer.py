@@ -80,6 +80,11 @@ class BaseOptimizer(object):
             self.test = list(self.MPS.nodes_list)
         initial_lr = optional_parameters.rate_of_change
         test_feature, test_label = data_source.test_data
+        # the test set goes to the device once, and the test metrics are evaluated with the weights the sweep left on the device
+        # (the reference feeds the NumPy test set and every weight tensor to the graph each step)
+        test_kind, _ = dev.feature_layout(test_feature, self.MPS.input_size, self.MPS.d_feature)
+        test_fm = nat.FM_PRECOMPUTED if test_kind == "phi" else self.feature_map
+        test_dev = None
         for i in range(n_step):
             start = time.time()
             rate_of_change = initial_lr / np.sqrt(1 - self.lr_reg ** (i + 1))      # baseoptimizer.py:109
@@ -88,11 +93,14 @@ class BaseOptimizer(object):
             self.bind_batch(batch_feature, batch_label, weights=self.test)
             self.rate_of_change = rate_of_change
             train_acc = self.train_step()
-            self.test = self._state.get_nodes()
+            self.test = self._state.get_nodes()                  # NumPy copies: the reference's self.test, and what save() writes
             self.MPS.create_feed_dict(self.test)
+            self._state_holds = self.test                        # the device already holds these weights: bind_batch skips the upload
             train_f = dev.predict(self._state.weights_view(), self._state.feat, self._state.feature_map, self.MPS.round)
             train_c = self.MPS.cost(train_f, batch_label)
-            test_prediction = self.MPS.predict(test_feature)
+            if test_dev is None:
+                test_dev = dev._as_device_f32(test_feature, self._state.device)
+            test_prediction = dev.predict(self._state.weights_view(), test_dev, test_fm, self.MPS.round).cpu().numpy()
             test_c = self.MPS.cost(test_prediction, test_label)
             test_acc = self.MPS.accuracy(test_prediction, test_label)
             test_conf = self.MPS.confusion_matrix(test_prediction, test_label)
@@ -111,8 +119,12 @@ class BaseOptimizer(object):
         """Feed one batch: the placeholders self._feature / self._label of the reference (baseoptimizer.py:44-45)."""
         weights = self.MPS.nodes_list if weights is None else weights
         kind, batch = dev.feature_layout(feature, self.MPS.input_size, self.MPS.d_feature)
+        prev = self._state
         st = self._ensure_state(batch, kind, weights)
-        st.set_nodes(weights, self.MPS._special_node_loc)
+        if not (st is prev and getattr(self, "_state_holds", None) is weights and weights is not None
+                and st.loc == self.MPS._special_node_loc):
+            st.set_nodes(weights, self.MPS._special_node_loc)
+        self._state_holds = None
         st.set_batch(feature, label)
         self._feature, self._label = st.feat, st.labels
 
