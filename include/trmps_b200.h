@@ -178,7 +178,8 @@ typedef struct {
 int         trmps_abi_version(void);
 const char* trmps_last_error(void);
 int         trmps_device_check(int device);             /* TRMPS_OK if `device` is an sm_100 GPU */
-int         trmps_set_option(int32_t option, int32_t value); /* option 0: gradient kernel, 1: forward kernel, 2: inference chain; value 0 = tcgen05 (default), 1 = FP32 SIMT;
+int         trmps_set_option(int32_t option, int32_t value); /* option 0: gradient kernel, 1: forward kernel, 2: inference chain; value 0 = tcgen05 (default for 1 and 2), 1 = FP32 SIMT;
+                                                            option 0 value 2 (default): gradient with fp16 hi/lo operands on the fp16 tensor pipe, 0: 3xTF32 operands;
                                                             option 2 value 2: fused tensor-core chain even for chains so long that its accumulated
                                                             rounding bias is estimated above 9e-5 (value 0 then uses the per-site FP32 path);
                                                             option 3: tile shape of the flat datasource kernel (development switch, 0 = default);

@@ -116,26 +116,44 @@ __global__ void grad_scale_kernel(const float* __restrict__ e_near, const float*
                                   int32_t* __restrict__ a_out, int32_t* __restrict__ gmax) {
   const int lane = threadIdx.x & 31;
   const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int n4 = Ds >> 2;                      // Ds is a multiple of 8: rows are read as float4 (two images per pass: four rows in flight)
   int best = 0;
-  for (int64_t t = gw; t < B; t += nw) {
-    float mn = 0.f, mf = 0.f, ms = 0.f;
-    for (int i = lane; i < Ds; i += 32) {
-      mn = fmaxf(mn, fabsf(__ldg(e_near + t * Ds + i)));
-      mf = fmaxf(mf, fabsf(__ldg(e_far + t * Ds + i)));
+  for (int64_t t0 = 2 * gw; t0 < B; t0 += 2 * nw) {
+    float mn[2] = {0.f, 0.f}, mf[2] = {0.f, 0.f}, ms[2] = {0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int64_t t = t0 + q;
+      if (t < B) {
+        for (int i = lane; i < n4; i += 32) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(e_near + t * Ds) + i);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(e_far + t * Ds) + i);
+          mn[q] = fmaxf(mn[q], fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+          mf[q] = fmaxf(mf[q], fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+        }
+        for (int i = lane; i < L2; i += 32) ms[q] = fmaxf(ms[q], fabsf(__ldg(sres + t * L2 + i)));
+      }
     }
-    for (int i = lane; i < L2; i += 32) ms = fmaxf(ms, fabsf(__ldg(sres + t * L2 + i)));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      mn = fmaxf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      mf = fmaxf(mf, __shfl_xor_sync(0xffffffffu, mf, o));
-      ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, o));
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        mn[q] = fmaxf(mn[q], __shfl_xor_sync(0xffffffffu, mn[q], o));
+        mf[q] = fmaxf(mf[q], __shfl_xor_sync(0xffffffffu, mf[q], o));
+        ms[q] = fmaxf(ms[q], __shfl_xor_sync(0xffffffffu, ms[q], o));
+      }
     }
-    const float2 ph = __ldg(reinterpret_cast<const float2*>(phi_near) + t);
-    const float mp = mn * fmaxf(fabsf(ph.x), fabsf(ph.y)), mw = ms * mf;
-    int a = 0;
-    if (mp > 0.f && mp < 3.0e38f) a = max(-100, min(100, exponent_of(mp) - GH_TA));
-    if (lane == 0) a_out[t] = a;
-    if (mw > 0.f && mw < 3.0e38f) best = max(best, exponent_of(mw) + a + GH_BIAS);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int64_t t = t0 + q;
+      if (t < B) {
+        const float2 ph = __ldg(reinterpret_cast<const float2*>(phi_near) + t);
+        const float mp = mn[q] * fmaxf(fabsf(ph.x), fabsf(ph.y)), mw = ms[q] * mf[q];
+        int a = 0;
+        if (mp > 0.f && mp < 3.0e38f) a = max(-100, min(100, exponent_of(mp) - GH_TA));
+        if (lane == 0) a_out[t] = a;
+        if (mw > 0.f && mw < 3.0e38f) best = max(best, exponent_of(mw) + a + GH_BIAS);
+      }
+    }
   }
   if (lane == 0 && best > 0) atomicMax(gmax, best);
 }
@@ -185,18 +203,35 @@ __global__ void __launch_bounds__(GH_THREADS, 1) grad_h_kernel(GradHArgs g) {
     const float* fac = side == 0 ? g.phi_near : g.sres;
     const int fstride = side == 0 ? 2 : L2;
     const int gexp = grad_exponent(g.gmax);
+    // Loads of a stage: branch-free (the image index is clamped, the tail is masked when the values are used) and nothing
+    // is computed from them here -- with `if (t < tend) { load; scale }` every one of the eight images became a branch with a
+    // dependent FMUL behind its loads, i.e. eight exposed L2 round trips per stage (ncu: 60 % of the kernel's stall samples on the
+    // long scoreboard, tensor pipe 28 % active)
     float4 v[8];
-    float f[8];
+    float fr[8];
+    int ar[8];
+    // (image t0 = first image of this thread in the stage; whole stages inside the range take the pointer path: one 64-bit
+    //  multiply per stage instead of three per image -- the producers are issue bound once the loads overlap)
     auto load_stage = [&](int ch) {
+      const int64_t t0 = tbeg + (int64_t)ch * GH_KCH + kgrp * 8;
+      if (t0 + 8 <= tend) {
+        const float* pe = env + t0 * Ds + lowidx;
+        const float* pf = fac + t0 * fstride + hiidx;
+        const int32_t* pa = g.a_t + t0;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int64_t t = tbeg + (int64_t)ch * GH_KCH + kgrp * 8 + u;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        f[u] = 0.f;
-        if (valid && t < tend) {
+        for (int u = 0; u < 8; ++u) {
+          v[u] = __ldg(reinterpret_cast<const float4*>(pe + u * Ds));
+          ar[u] = __ldg(pa + u);
+          fr[u] = __ldg(pf + u * fstride);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          int64_t t = t0 + u;
+          t = t < tend ? t : tend - 1;
           v[u] = __ldg(reinterpret_cast<const float4*>(env + t * Ds + lowidx));
-          const int a = __ldg(g.a_t + t);
-          f[u] = scale_pow2(__ldg(fac + t * fstride + hiidx), side == 0 ? -a : a - gexp);
+          ar[u] = __ldg(g.a_t + t);
+          fr[u] = __ldg(fac + t * fstride + hiidx);
         }
       }
     };
@@ -205,6 +240,13 @@ __global__ void __launch_bounds__(GH_THREADS, 1) grad_h_kernel(GradHArgs g) {
       const int s = ch % GH_STAGES, it = ch / GH_STAGES;
       uint8_t* tile_hi = smem + s * GH_STAGE_BYTES + side * 2 * GH_PART_BYTES, *tile_lo = tile_hi + GH_PART_BYTES;
       if (ch >= GH_STAGES) mbar_wait(&bars[s], (uint32_t)((it - 1) & 1));   // MMAs that read this stage are done
+      float f[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t t = tbeg + (int64_t)ch * GH_KCH + kgrp * 8 + u;
+        const float sc = scale_pow2(fr[u], side == 0 ? -ar[u] : ar[u] - gexp);
+        f[u] = (valid && t < tend) ? sc : 0.f;
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         __align__(16) __half2 h2[4];

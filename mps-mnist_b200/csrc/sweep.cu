@@ -50,7 +50,7 @@ ProfScope::~ProfScope() {
   ++g_prof_n;
 }
 
-static int g_grad_impl = 0;   // 0 = tcgen05 3xTF32, 1 = FP32 SIMT
+static int g_grad_impl = 2;   // 2 = tcgen05 fp16 hi/lo (default; shapes it does not cover take 0), 0 = tcgen05 3xTF32, 1 = FP32 SIMT
 static int g_fwd_impl = 0;    // same for the forward contraction
 static int g_chain_impl = 0;  // 0 = fused tcgen05 chain for inference when Ds <= 32, 1 = per-site FP32 SIMT steps
 static int g_fwd_site = 1;    // first forward of a two-site update in its single-site form (needs the cached environment of the same site: trmps_sweep_init_env / sweeps provide it)

@@ -144,7 +144,8 @@ def profile_end():
     return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(PROF_CATEGORIES)}
 
 
-OPT_GRAD_IMPL, GRAD_TCGEN05, GRAD_SIMT, GRAD_TCGEN05_F16 = 0, 0, 1, 2      # 0: 3xTF32 on tcgen05 (default), 2: fp16 hi/lo on tcgen05
+OPT_GRAD_IMPL, GRAD_TCGEN05, GRAD_SIMT, GRAD_TCGEN05_F16 = 0, 0, 1, 2      # 0: 3xTF32 on tcgen05, 2: fp16 hi/lo on tcgen05 (default)
+GRAD_DEFAULT = GRAD_TCGEN05_F16
 OPT_FWD_IMPL, FWD_TCGEN05, FWD_SIMT, FWD_TCGEN05_TF32 = 1, 0, 1, 2      # 0: fp16 hi/lo on tcgen05 (default), 2: 3xTF32 on tcgen05
 OPT_CHAIN_IMPL, CHAIN_TCGEN05, CHAIN_SIMT, CHAIN_TCGEN05_ALWAYS = 2, 0, 1, 2     # 0 falls back to 1 for chains whose rounding-bias estimate exceeds 9e-5
 

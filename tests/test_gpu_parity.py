@@ -412,7 +412,7 @@ def test_tcgen05_gradient_matches_simt_and_fp64(D, B):
         torch.cuda.synchronize()
         g_tc = st.grad_matrix().clone().cpu().numpy()
     finally:
-        nat.set_option(nat.OPT_GRAD_IMPL, nat.GRAD_TCGEN05)
+        nat.set_option(nat.OPT_GRAD_IMPL, nat.GRAD_DEFAULT)
     bond, (Cn, Cf, pn, pf) = oracle_bond_setup(nodes, loc, phi, L, +1)
     C = o.calculate_C(Cn, Cf, pn, pf).astype(np.float64)
     h = o.softmax(st.logits0().cpu().numpy().astype(np.float64))

@@ -23,4 +23,4 @@ for name, impl in (("3xTF32", nat.GRAD_TCGEN05), ("fp16 hi/lo", nat.GRAD_TCGEN05
     nat.set_option(nat.OPT_GRAD_IMPL, impl)
     both = t_of(lambda: st.bond_gradient(loc, +1, opt))
     print("%-10s forward+loss+gradient %.3f ms -> loss+gradient %.3f ms" % (name, both, both - fwd))
-nat.set_option(nat.OPT_GRAD_IMPL, nat.GRAD_TCGEN05)
+nat.set_option(nat.OPT_GRAD_IMPL, nat.GRAD_DEFAULT)
