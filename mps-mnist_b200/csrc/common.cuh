@@ -142,6 +142,7 @@ int launch_sum_round_logits(const float* fpart, int nsplit, int64_t B, int L, in
 int launch_phi_site(const float* feat_site, int fm, int64_t B, float* out, cudaStream_t st);
 int launch_phi_pair(const float* feat_a, const float* feat_b, int fm, int64_t B, float* out_a, float* out_b, cudaStream_t st);
 
+constexpr int TRMPS_IMG_BLOCK = 256;      // images per CTA of the per-image kernels (loss, armijo); `red` has a row per CTA (128 was measured slower: scalar 17 -> 23 ms per cfg3 step)
 struct LossArgs {
   const float* fpart; int nsplit; float* f0; const float* labels; const float* phi_far;
   float* resid; float* sres; float* hres; float* red; int64_t B; int L; int loss_kind; int from_parts;

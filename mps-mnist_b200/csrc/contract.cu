@@ -331,8 +331,8 @@ __device__ __forceinline__ void fixed_order_reduce(const float* __restrict__ red
 }
 // arrival of this CTA at a self-resetting counter; true in every thread of the last CTA to arrive
 __device__ __forceinline__ bool last_cta_arrives(int32_t* counter, int* s_flag) {
-  __threadfence();
-  __syncthreads();
+  if (threadIdx.x < 32) __threadfence();          // the per-CTA partials are written by threads of warp 0 only: the other warps' (large) output
+  __syncthreads();                                //   stores need not drain before this CTA announces itself
   if (threadIdx.x == 0) {
     const int old = atomicAdd(counter, 1);
     const int last = old == (int)gridDim.x - 1;
@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(256) armijo_kernel(ArmijoArgs a) {
   __syncthreads();
   if (threadIdx.x < 19) {
     float s = 0.f;
-    for (int i = 0; i < 8; ++i) s += swarp[i][threadIdx.x];
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += swarp[i][threadIdx.x];
     __stcg(&a.red[blockIdx.x * 32 + threadIdx.x], s);
   }
   // the last CTA to arrive: the 19 trial sums in a fixed order and, on a single rank, the decision itself
@@ -772,13 +772,13 @@ int launch_merge(const float* special, const float* far_node, float* M, int Ds, 
 // launch helpers used by sweep.cu
 int launch_loss(const LossArgs& a, cudaStream_t st) {
   if (a.B == 0) return TRMPS_OK;
-  loss_kernel<<<(unsigned)ceil_div64(a.B, 256), 256, 0, st>>>(a);
+  loss_kernel<<<(unsigned)ceil_div64(a.B, TRMPS_IMG_BLOCK), TRMPS_IMG_BLOCK, 0, st>>>(a);
   TRMPS_LAUNCH_OK("loss_kernel");
   return TRMPS_OK;
 }
 int launch_armijo(const ArmijoArgs& a, cudaStream_t st) {
   if (a.B == 0) return TRMPS_OK;
-  armijo_kernel<<<(unsigned)ceil_div64(a.B, 256), 256, 0, st>>>(a);
+  armijo_kernel<<<(unsigned)ceil_div64(a.B, TRMPS_IMG_BLOCK), TRMPS_IMG_BLOCK, 0, st>>>(a);
   TRMPS_LAUNCH_OK("armijo_kernel");
   return TRMPS_OK;
 }

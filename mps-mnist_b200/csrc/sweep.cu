@@ -118,7 +118,7 @@ static int compute_layout(int32_t N, int64_t B, int32_t L, int32_t Ds, int32_t s
   o->phi2 = off; off += a4(4 * B);
   o->Ut = off; off += a4(R * R);
   o->sv = off; off += a4(3 * R);
-  int64_t rr = (B + 255) / 256;
+  int64_t rr = (B + TRMPS_IMG_BLOCK - 1) / TRMPS_IMG_BLOCK;      // one row per CTA of the per-image kernels
   if (rr < 296) rr = 296;
   o->red = off; off += a4(rr * 32);
   o->scal = off; off += a4(2 * TRMPS_S_COUNT);
