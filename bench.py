@@ -659,7 +659,8 @@ def run_ours(args, rank, local_rank, world):
                             "of them (`executed_fraction`)", bound="tensor", avg_launch_ms=fwd_ms / max(fwd_n, 1), launches=fwd_n,
                      achieved=flops_launch * fwd_n / max(fwd_ms * 1e-3, 1e-12) / 1e12, peak=tf32_peak, unit="TFLOP/s", executed_fraction=0.75,
                      traffic=61.7e6 if (B == 60000 and D == 120) else None, share_of_step=fwd_ms / ms_total),
-        gradient=dict(kernel="grad_tc_kernel (+ split-K sum): G = P^T W over the batch, tcgen05 kind::tf32, 3xTF32", bound="tensor",
+        gradient=dict(kernel="grad_scale_kernel + grad_h_kernel + sum_parts_scaled_kernel: G = P^T W over the batch, tcgen05 kind::f16 with fp16 hi/lo operands "
+                             "(3 products per FP32 product; 3xTF32 grad_tc_kernel with trmps_set_option(0, 0))", bound="tensor",
                       avg_launch_ms=grad_ms / max(grad_n, 1), launches=grad_n,
                       achieved=flops_launch * grad_n / max(grad_ms * 1e-3, 1e-12) / 1e12, peak=tf32_peak, unit="TFLOP/s",
                       traffic=62.9e6 if (B == 60000 and D == 120) else None, share_of_step=grad_ms / ms_total),
