@@ -31,6 +31,7 @@ constexpr int SVD_WARPS = SVD_THREADS / 32;
 
 struct SvdArgs {
   float* M; float* Ut; int R, Cc, Ds; const int32_t* d_near; int32_t* iscal; int32_t* rowmap; float* norms;
+  float* norms2;     // second buffer of the current squared norms: sweep s writes buffer (s + 1) & 1 and reads buffer s & 1 (no CTA reads what another one is rewriting)
   float tol; int max_sweeps; int keep; float* dbg;   // keep: rows that can survive the truncation (max_size); dbg: 8 floats, phase cycle counters of CTA 0 (load, gram, rotate, replay, store, grid sync)
 };
 
@@ -409,7 +410,8 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
     // loop may only stop on the kept rows' criterion while n_bot * w < 7 (nothing there can belong to the top m).
     if (tid == 0) { theta_s = 0.f; nbot_s = 0; }
     if (sweep > 0 && a.keep < Ra) {
-      for (int i = tid; i < Ra; i += CL_THREADS) cn_s[i] = __ldcg(&a.norms[i]);
+      const float* nsrc = (sweep & 1) ? a.norms2 : a.norms;          // written during the previous sweep
+      for (int i = tid; i < Ra; i += CL_THREADS) cn_s[i] = __ldcg(&nsrc[i]);
       __syncthreads();
       for (int i = tid; i < Ra; i += CL_THREADS) {
         const float c = cn_s[i];
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(CL_THREADS) svd_jacobi_cluster_kernel(SvdClArg
         const int y = x + rem;
         Gs[0][x][y] = s;
         Gs[0][y][x] = s;
-        if (x == y && crank == 0 && srow[x] >= 0) a.norms[srow[x]] = s;      // current squared norm, by rank
+        if (x == y && crank == 0 && srow[x] >= 0) (((sweep + 1) & 1) ? a.norms2 : a.norms)[srow[x]] = s;      // current squared norm, by rank
       }
       __syncthreads();
       tick(1);
@@ -785,6 +787,7 @@ int svd_split(const trmps_sweep* s, const trmps_layout& lay, const BondGeom& g, 
   a.Ut = s->work + lay.Ut;
   a.R = R; a.Cc = Cc; a.Ds = Ds; a.d_near = g.d_near; a.iscal = s->iwork;
   a.norms = s->work + lay.sv;
+  a.norms2 = s->work + lay.red + 1024;      // (red: 8 debug floats, the hand-over flags from +32, then this)
   a.rowmap = reinterpret_cast<int32_t*>(s->work + lay.sv + 2 * R);
   a.tol = 5.9604645e-8f * sqrtf((float)Cc);
   a.dbg = s->work + lay.red;
