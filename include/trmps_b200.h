@@ -129,8 +129,10 @@ typedef struct {
   int64_t sv;                            /* 3R: singular values (descending), int32 order, int32 row map */
   int64_t red;                           /* per-CTA partial sums of the scalar reductions */
   int64_t scal;                          /* TRMPS_S_COUNT floats */
-  int64_t bimg;                          /* TF32 hi/lo shared-memory images of the bond for the tensor-core forward */
-  int64_t split_ws;                      /* FP64 Gram partials, Gram matrix, Cholesky factor and the rotated factor of the split */
+  int64_t bimg;                          /* hi/lo shared-memory images of the bond for the tensor-core forward, the bond's power-of-two exponent word,
+                                            arrival counters and the partial logits of the forward's column-split tail tiles */
+  int64_t split_ws;                      /* FP64 Gram partials (added by the cluster Cholesky itself), Gram matrix and FP64 factor (single-SM Cholesky
+                                            only), FP32 factor and the rotated factor of the split */
   int64_t env_img;                       /* fp16 hi/lo images of up to N node matrices for the tensor-core environment chain */
   int64_t total;                         /* floats the caller must allocate for `work` */
   int32_t gsplit, nsplit;                /* split-K factor of the gradient, column split of the forward */
